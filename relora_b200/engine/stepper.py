@@ -1,0 +1,129 @@
+"""The per-update machinery shared by the trainer and ``bench.py``.
+
+A *stepper* owns the model replica, the flat parameter store, the optimizer and the gradient
+transport and exposes two calls:
+
+    loss = stepper.micro_step(input_ids)      # forward + backward, gradients accumulate locally
+    info = stepper.update(lr=None)            # reduce (once), clip, AdamW, zero grads
+
+This mirrors one iteration of the reference hot loop (``torchrun_main.py:783-826``) with the
+gradient all-reduce hoisted out of the accumulation loop.  :class:`ModuleStepper` drives any
+``nn.Module`` whose forward returns ``.loss`` (CPU/gloo and the generic GPU path);
+:class:`relora_b200.engine.fused_llama.FusedLlamaStepper` is the B200 executor (whole-layer fused
+kernels, CUDA graphs) with the same interface.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ..parallel.dist import DistInfo
+from ..parallel.flat import FlatAdamW, FlatParamStore
+from ..parallel.grad_sync import GradSync, broadcast_params
+
+__all__ = ["UpdateInfo", "ModuleStepper", "trainable_named_parameters", "make_stepper"]
+
+
+@dataclass
+class UpdateInfo:
+    grad_norm: torch.Tensor  # device scalar (norm of the averaged gradient, before clipping)
+    skipped: bool
+
+
+def trainable_named_parameters(model: torch.nn.Module) -> List[Tuple[str, torch.nn.Parameter]]:
+    return [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+
+
+class ModuleStepper:
+    def __init__(
+        self,
+        model: torch.nn.Module,
+        info: DistInfo,
+        *,
+        lr: float,
+        betas=(0.9, 0.999),
+        eps: float = 1e-8,
+        weight_decay: float = 0.0,
+        clip_grad_norm: float = 1.0,
+        grad_accumulation: int = 1,
+        zero: bool = False,
+        transport: str = "nccl",
+        native=None,
+        symm_factory=None,
+    ):
+        self.model, self.info = model, info
+        self.ga = grad_accumulation
+        self.clip = clip_grad_norm
+        broadcast_params(model)
+        named = trainable_named_parameters(model)
+        allocator = symm_factory.allocator() if (symm_factory is not None and transport == "p2p") else None
+        self.store = FlatParamStore(named, world_size=info.world_size, allocator=allocator)
+        symm = symm_factory.bind(self.store) if (symm_factory is not None and transport == "p2p") else None
+        self.sync = GradSync(self.store, info, transport=transport, zero=zero, symm=symm)
+        shard = self.sync.shard if zero else None
+        self.optimizer = FlatAdamW(self.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                   shard=shard, native=native)
+        self.trainable_params = [p for _, p in named]
+        self.trainable_names = [n for n, _ in named]
+        self.lora_params = [p for n, p in named if "lora_" in n]
+
+    # ------------------------------------------------------------------ one micro-batch
+    def micro_step(self, input_ids: torch.Tensor) -> torch.Tensor:
+        out = self.model(input_ids=input_ids, labels=input_ids)
+        loss = out.loss
+        (loss / self.ga).backward()
+        return loss.detach()
+
+    @torch.no_grad()
+    def eval_loss(self, input_ids: torch.Tensor) -> torch.Tensor:
+        return self.model(input_ids=input_ids, labels=input_ids).loss.detach()
+
+    # ------------------------------------------------------------------ one optimizer update
+    @torch.no_grad()
+    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
+        self.sync.reduce()
+        total, scale = self.sync.grad_norm_and_scale(self.clip)
+        if error_if_nonfinite and not bool(torch.isfinite(total)):
+            raise RuntimeError(
+                f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped."
+            )
+        skipped = bool(skip) if skip is not None and not self.store.params.is_cuda else False
+        self.optimizer.step(grad_scale=scale, skip=skip)
+        self.sync.gather_params()
+        self.optimizer.zero_grad()
+        return UpdateInfo(total, skipped)
+
+    def set_lr(self, lr: float) -> None:
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr
+
+
+def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None):
+    """Pick the executor for ``model`` on ``info.device`` according to ``--engine``."""
+    engine = getattr(args, "engine", "auto")
+    zero = str(args.optimizer).lower() == "adam_zero"
+    transport = getattr(args, "comm", "auto")
+    if transport == "auto":
+        transport = "nccl"
+    kw = dict(
+        lr=args.lr,
+        betas=(args.adam_beta1, args.adam_beta2),
+        weight_decay=args.weight_decay,
+        clip_grad_norm=args.clip_grad_norm,
+        grad_accumulation=args.gradient_accumulation,
+        zero=zero,
+        transport=transport,
+        native=native,
+        symm_factory=symm_factory,
+    )
+    if engine in ("auto", "fused") and info.device.type == "cuda":
+        from .fused_llama import FusedLlamaStepper, supports
+
+        ok, why = supports(model, args)
+        if ok:
+            return FusedLlamaStepper(model, info, cuda_graphs=getattr(args, "cuda_graphs", True), **kw)
+        if engine == "fused":
+            raise RuntimeError(f"--engine fused requested but not applicable: {why}")
+    return ModuleStepper(model, info, **kw)
