@@ -1,0 +1,288 @@
+// Python bindings (pybind11 over torch::Tensor) for the sm_100a kernels.  Every function launches on the
+// current PyTorch CUDA stream, so the ops compose with torch streams and CUDA-graph capture.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gemm.h"
+#include "kernels.h"
+
+namespace rb {
+extern long long g_launch_count;
+}
+
+namespace {
+
+using torch::Tensor;
+using OptTensor = c10::optional<Tensor>;
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void chk_bf16(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bfloat16");
+}
+void chk_2d_rowmajor(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 2 && t.stride(1) == 1, name, " must be 2-D with unit inner stride");
+}
+const uint32_t* u32ptr(const OptTensor& t) {
+  if (!t.has_value()) return nullptr;
+  TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kInt, "seed tensor must be a CUDA int32 tensor");
+  return reinterpret_cast<const uint32_t*>(t->data_ptr<int32_t>());
+}
+const float* f32ptr(const OptTensor& t) {
+  if (!t.has_value()) return nullptr;
+  TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat, "expected a CUDA float32 tensor");
+  return t->data_ptr<float>();
+}
+
+rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
+  chk_bf16(t, name);
+  chk_2d_rowmajor(t, name);
+  rb::Operand o;
+  o.ptr = t.data_ptr();
+  o.ld = t.stride(0);
+  o.mn_major = mn_major;
+  return o;
+}
+
+// out[M,N] = alpha*(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)
+void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
+          int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
+          const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k) {
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::GemmDesc d;
+  d.a1 = operand(a1, a1_mn, "a1");
+  d.b1 = operand(b1, b1_mn, "b1");
+  d.M = (int)M; d.N = (int)N; d.K1 = (int)K1; d.K2 = (int)K2;
+  if (K2 > 0) {
+    TORCH_CHECK(a2.has_value() && b2.has_value(), "a2/b2 required when K2 > 0");
+    d.a2 = operand(*a2, false, "a2");
+    d.b2 = operand(*b2, false, "b2");
+  }
+  d.n_per_group = (int)n_per_group; d.a1_group_kofs = (int)a1_group_kofs; d.a2_group_kofs = (int)a2_group_kofs;
+  TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.stride(1) == 1, "out must be 2-D row-major CUDA");
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16 || out.scalar_type() == at::kFloat, "out must be bf16 or fp32");
+  TORCH_CHECK(out.size(0) >= M && out.size(1) >= N, "out too small");
+  d.out = out.data_ptr(); d.ldc = out.stride(0); d.out_f32 = out.scalar_type() == at::kFloat;
+  d.accumulate = accumulate; d.alpha = (float)alpha; d.block_n = (int)block_n; d.split_k = (int)split_k;
+  if (residual.has_value()) {
+    chk_bf16(*residual, "residual");
+    chk_2d_rowmajor(*residual, "residual");
+    d.residual = residual->data_ptr(); d.ldr = residual->stride(0);
+  }
+  rb::gemm_bf16(d, cur_stream());
+}
+
+void rmsnorm_fwd(const Tensor& x, const Tensor& w, Tensor& y, Tensor& rstd, double eps, const OptTensor& xd, const OptTensor& seed,
+                 std::vector<int64_t> keys, double p) {
+  chk_bf16(x, "x"); chk_bf16(w, "w"); chk_bf16(y, "y");
+  TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && w.is_contiguous(), "rmsnorm: contiguous tensors required");
+  const int H = (int)x.size(-1);
+  const int M = (int)(x.numel() / H);
+  c10::cuda::CUDAGuard guard(x.device());
+  uint32_t k[4] = {0, 0, 0, 0};
+  int G = 0;
+  void* xdp = nullptr;
+  if (xd.has_value()) {
+    chk_bf16(*xd, "xd");
+    TORCH_CHECK(xd->is_contiguous(), "xd must be contiguous");
+    G = (int)keys.size();
+    TORCH_CHECK(G >= 1 && G <= 4 && xd->numel() == (int64_t)M * G * H, "xd must be [M, G*H]");
+    for (int i = 0; i < G; ++i) k[i] = (uint32_t)keys[i];
+    xdp = xd->data_ptr();
+  }
+  const uint32_t thr = (uint32_t)llround(p * 16777216.0);
+  rb::rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), M, H, (float)eps, xdp, G, u32ptr(seed), k, thr,
+                  (float)(1.0 / (1.0 - p)), cur_stream());
+}
+
+void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tensor& rstd, const OptTensor& dx_add, Tensor& dx, Tensor& dw) {
+  chk_bf16(dy, "dy"); chk_bf16(x, "x"); chk_bf16(w, "w"); chk_bf16(dx, "dx");
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be fp32");
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous(), "rmsnorm_bwd: contiguous tensors required");
+  const int H = (int)x.size(-1);
+  const int M = (int)(x.numel() / H);
+  c10::cuda::CUDAGuard guard(x.device());
+  const void* add = nullptr;
+  if (dx_add.has_value()) { chk_bf16(*dx_add, "dx_add"); TORCH_CHECK(dx_add->is_contiguous()); add = dx_add->data_ptr(); }
+  rb::rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), add, dx.data_ptr(), dw.data_ptr<float>(), M, H,
+                  cur_stream());
+}
+
+void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vector<int64_t> keys, double p) {
+  chk_bf16(x, "x"); chk_bf16(xd, "xd");
+  TORCH_CHECK(x.is_contiguous() && xd.is_contiguous());
+  const int H = (int)x.size(-1);
+  const int M = (int)(x.numel() / H);
+  const int G = (int)keys.size();
+  TORCH_CHECK(xd.numel() == (int64_t)M * G * H, "xd must be [M, G*H]");
+  uint32_t k[4] = {0, 0, 0, 0};
+  for (int i = 0; i < G && i < 4; ++i) k[i] = (uint32_t)keys[i];
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::dropout_expand(x.data_ptr(), xd.data_ptr(), M, H, G, u32ptr(seed), k, (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)),
+                     cur_stream());
+}
+
+void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, const OptTensor& seed, std::vector<int64_t> keys, double p) {
+  chk_bf16(parts, "parts"); chk_bf16(out, "out");
+  TORCH_CHECK(parts.dim() == 3 && parts.is_contiguous() && out.is_contiguous(), "parts must be contiguous [G, M, H]");
+  const int G = (int)parts.size(0), M = (int)parts.size(1), H = (int)parts.size(2);
+  TORCH_CHECK((int)keys.size() == G && out.numel() == (int64_t)M * H);
+  uint32_t k[4] = {0, 0, 0, 0};
+  for (int i = 0; i < G && i < 4; ++i) k[i] = (uint32_t)keys[i];
+  const void* bp = nullptr;
+  if (base.has_value()) { chk_bf16(*base, "base"); TORCH_CHECK(base->is_contiguous()); bp = base->data_ptr(); }
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::dropout_combine(bp, parts.data_ptr(), (long long)M * H, out.data_ptr(), M, H, G, u32ptr(seed), k,
+                      (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
+}
+
+void rope_inplace(Tensor& buf, int64_t T, int64_t n_rot_heads, int64_t hd, int64_t rotary_dim, const Tensor& cos, const Tensor& sin,
+                  bool backward, int64_t pos0) {
+  chk_bf16(buf, "buf"); chk_bf16(cos, "cos"); chk_bf16(sin, "sin");
+  chk_2d_rowmajor(buf, "buf");
+  TORCH_CHECK(cos.is_contiguous() && sin.is_contiguous() && cos.size(-1) == rotary_dim, "cos/sin must be [n_pos, rotary_dim]");
+  TORCH_CHECK(T + pos0 <= cos.size(0), "rotary table too short");
+  c10::cuda::CUDAGuard guard(buf.device());
+  rb::rope_inplace(buf.data_ptr(), buf.stride(0), (int)buf.size(0), (int)T, (int)n_rot_heads, (int)hd, (int)rotary_dim, cos.data_ptr(),
+                   sin.data_ptr(), backward, (int)pos0, cur_stream());
+}
+
+void swiglu_fwd(const Tensor& gu, Tensor& h) {
+  chk_bf16(gu, "gu"); chk_bf16(h, "h"); chk_2d_rowmajor(gu, "gu"); chk_2d_rowmajor(h, "h");
+  const int F = (int)h.size(1);
+  TORCH_CHECK(gu.size(1) == 2 * F && gu.size(0) == h.size(0));
+  c10::cuda::CUDAGuard guard(gu.device());
+  rb::swiglu_fwd(gu.data_ptr(), gu.stride(0), h.data_ptr(), h.stride(0), (int)h.size(0), F, cur_stream());
+}
+void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
+  chk_bf16(dh, "dh"); chk_bf16(gu, "gu"); chk_bf16(dgu, "dgu");
+  chk_2d_rowmajor(dh, "dh"); chk_2d_rowmajor(gu, "gu"); chk_2d_rowmajor(dgu, "dgu");
+  const int F = (int)dh.size(1);
+  TORCH_CHECK(gu.size(1) == 2 * F && dgu.size(1) == 2 * F);
+  c10::cuda::CUDAGuard guard(gu.device());
+  rb::swiglu_bwd(dh.data_ptr(), dh.stride(0), gu.data_ptr(), gu.stride(0), dgu.data_ptr(), dgu.stride(0), (int)dh.size(0), F, cur_stream());
+}
+
+void embedding_fwd(const Tensor& ids, const Tensor& table, Tensor& out) {
+  chk_bf16(table, "table"); chk_bf16(out, "out");
+  TORCH_CHECK(ids.is_cuda() && ids.scalar_type() == at::kLong && ids.is_contiguous() && table.is_contiguous() && out.is_contiguous());
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::embedding_fwd(ids.data_ptr<int64_t>(), table.data_ptr(), out.data_ptr(), (int)ids.numel(), (int)table.size(1), cur_stream());
+}
+void embedding_bwd(const Tensor& ids, const Tensor& dout, Tensor& dtable, int64_t padding_idx) {
+  chk_bf16(dout, "dout");
+  TORCH_CHECK(dtable.scalar_type() == at::kFloat && dtable.is_contiguous() && dout.is_contiguous() && ids.is_contiguous());
+  c10::cuda::CUDAGuard guard(dout.device());
+  rb::embedding_bwd(ids.data_ptr<int64_t>(), dout.data_ptr(), dtable.data_ptr<float>(), (int)ids.numel(), (int)dtable.size(1), padding_idx,
+                    cur_stream());
+}
+
+void cross_entropy_fwd_bwd(Tensor& logits, const Tensor& labels, int64_t V, double grad_scale, int64_t ignore_index, Tensor& loss_sum,
+                           Tensor& count) {
+  chk_bf16(logits, "logits"); chk_2d_rowmajor(logits, "logits");
+  TORCH_CHECK(labels.is_cuda() && labels.scalar_type() == at::kLong && labels.is_contiguous() && labels.numel() == logits.size(0));
+  TORCH_CHECK(loss_sum.scalar_type() == at::kFloat && count.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(logits.device());
+  rb::cross_entropy_fwd_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr<int64_t>(), (int)logits.size(0), (int)V, (float)grad_scale,
+                            ignore_index, loss_sum.data_ptr<float>(), count.data_ptr<float>(), cur_stream());
+}
+
+void transpose(const Tensor& in, Tensor& out) {
+  chk_bf16(in, "in"); chk_bf16(out, "out"); chk_2d_rowmajor(in, "in"); chk_2d_rowmajor(out, "out");
+  TORCH_CHECK(out.size(0) == in.size(1) && out.size(1) == in.size(0));
+  c10::cuda::CUDAGuard guard(in.device());
+  rb::transpose_bf16(in.data_ptr(), in.stride(0), out.data_ptr(), out.stride(0), (int)in.size(0), (int)in.size(1), cur_stream());
+}
+void add(const Tensor& a, const Tensor& b, Tensor& out) {
+  chk_bf16(a, "a"); chk_bf16(b, "b"); chk_bf16(out, "out");
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && out.is_contiguous() && a.numel() == b.numel() && a.numel() == out.numel());
+  c10::cuda::CUDAGuard guard(a.device());
+  rb::add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), cur_stream());
+}
+void cast_f32_to_bf16(const Tensor& in, Tensor& out, double scale) {
+  TORCH_CHECK(in.scalar_type() == at::kFloat && in.is_contiguous() && out.is_contiguous() && in.numel() == out.numel());
+  chk_bf16(out, "out");
+  c10::cuda::CUDAGuard guard(in.device());
+  rb::cast_f32_to_bf16(in.data_ptr<float>(), out.data_ptr(), in.numel(), (float)scale, cur_stream());
+}
+void fill_uniform_hash(Tensor& out, int64_t seed, double bound) {
+  chk_bf16(out, "out"); chk_2d_rowmajor(out, "out");
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::fill_uniform_hash(out.data_ptr(), (int)out.size(0), (int)out.size(1), out.stride(0), (uint32_t)seed, (float)bound, cur_stream());
+}
+void seed_advance(Tensor& seed) {
+  TORCH_CHECK(seed.is_cuda() && seed.scalar_type() == at::kInt && seed.numel() == 1);
+  c10::cuda::CUDAGuard guard(seed.device());
+  rb::seed_advance(reinterpret_cast<uint32_t*>(seed.data_ptr<int32_t>()), cur_stream());
+}
+
+void adamw_flat(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, double lr, double b1, double b2, double eps, double wd, int64_t step,
+                const OptTensor& grad_scale, double grad_scale_host, const OptTensor& skip) {
+  chk_bf16(p, "param");
+  TORCH_CHECK(p.is_contiguous() && g.is_contiguous() && m.is_contiguous() && v.is_contiguous());
+  TORCH_CHECK(g.numel() == p.numel() && m.numel() == p.numel() && v.numel() == p.numel());
+  const bool gf = g.scalar_type() == at::kFloat, sf = m.scalar_type() == at::kFloat;
+  TORCH_CHECK(gf || g.scalar_type() == at::kBFloat16, "grad must be bf16 or fp32");
+  TORCH_CHECK((sf || m.scalar_type() == at::kBFloat16) && m.scalar_type() == v.scalar_type(), "moments must be bf16 or fp32");
+  c10::cuda::CUDAGuard guard(p.device());
+  rb::adamw_flat(p.data_ptr(), g.data_ptr(), gf, m.data_ptr(), v.data_ptr(), sf, p.numel(), (float)lr, (float)b1, (float)b2, (float)eps,
+                 (float)wd, (int)step, f32ptr(grad_scale), (float)grad_scale_host, f32ptr(skip), cur_stream());
+}
+void sumsq(const Tensor& x, Tensor& out) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && out.scalar_type() == at::kFloat);
+  const bool f = x.scalar_type() == at::kFloat;
+  TORCH_CHECK(f || x.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::sumsq(x.data_ptr(), f, x.numel(), out.data_ptr<float>(), cur_stream());
+}
+void random_prune(Tensor& x, double ratio, int64_t seed, int64_t col_offset) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous());
+  const bool f = x.scalar_type() == at::kFloat;
+  TORCH_CHECK(f || x.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::random_prune(x.data_ptr(), f, x.numel(), (float)ratio, (uint32_t)seed, col_offset, cur_stream());
+}
+void magnitude_prune(Tensor& x, double ratio, Tensor& workspace, Tensor& thr) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && thr.scalar_type() == at::kFloat);
+  TORCH_CHECK((size_t)workspace.numel() * workspace.element_size() >= rb::magnitude_quantile_workspace_bytes(), "workspace too small");
+  const bool f = x.scalar_type() == at::kFloat;
+  TORCH_CHECK(f || x.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::magnitude_quantile(x.data_ptr(), f, x.numel(), (float)ratio, thr.data_ptr<float>(), workspace.data_ptr(), cur_stream());
+  rb::threshold_prune(x.data_ptr(), f, x.numel(), thr.data_ptr<float>(), cur_stream());
+}
+
+long long launch_count() { return rb::g_launch_count; }
+void reset_launch_count() { rb::g_launch_count = 0; }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "relora_b200 sm_100a kernels";
+  m.def("gemm", &gemm, "tcgen05 GEMM with fused LoRA K-extension");
+  m.def("gemm_clear_descriptor_cache", &rb::gemm_clear_descriptor_cache);
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("dropout_expand", &dropout_expand);
+  m.def("dropout_combine", &dropout_combine);
+  m.def("rope_inplace", &rope_inplace);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd", &embedding_bwd);
+  m.def("cross_entropy_fwd_bwd", &cross_entropy_fwd_bwd);
+  m.def("transpose", &transpose);
+  m.def("add", &add);
+  m.def("cast_f32_to_bf16", &cast_f32_to_bf16);
+  m.def("fill_uniform_hash", &fill_uniform_hash);
+  m.def("seed_advance", &seed_advance);
+  m.def("adamw_flat", &adamw_flat);
+  m.def("sumsq", &sumsq);
+  m.def("random_prune", &random_prune);
+  m.def("magnitude_prune", &magnitude_prune);
+  m.def("quantile_workspace_bytes", &rb::magnitude_quantile_workspace_bytes);
+  m.def("launch_count", &launch_count);
+  m.def("reset_launch_count", &reset_launch_count);
+}

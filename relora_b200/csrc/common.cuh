@@ -1,0 +1,117 @@
+// Shared device helpers: counter-based RNG (dropout masks / re-init), reductions, vector access,
+// plus the host-side launch counter and error macro used by every launcher.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace rb {
+
+// number of kernels launched by this extension since the last reset (bench.py: "gpu_launches")
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+inline void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define RB_CHECK_LAUNCH(name)                \
+  do {                                       \
+    rb::count_launch();                      \
+    rb::check(cudaGetLastError(), name);     \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
+
+}  // namespace rb
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+// keep(row, col) = (lowbias32(row*C1 ^ col*C2 ^ seed) >> 8) >= threshold24     (ops/reference.py)
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t hash_rc(uint32_t seed, uint32_t row, uint32_t col) {
+  return lowbias32((row * 0x9E3779B1u) ^ (col * 0x85EBCA77u) ^ seed);
+}
+__host__ __device__ __forceinline__ bool keep_bit(uint32_t seed, uint32_t row, uint32_t col, uint32_t threshold24) {
+  return (hash_rc(seed, row, col) >> 8) >= threshold24;
+}
+__host__ __device__ __forceinline__ uint32_t mix_seed(uint32_t base, uint32_t key) {
+  uint32_t x = base ^ key;
+  x = (x ^ (x >> 16)) * 0x7FEB352Du;
+  x = (x ^ (x >> 15)) * 0x846CA68Bu;
+  return x ^ (x >> 16);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `scratch` must hold >= 32 floats; result broadcast to every thread
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? scratch[lane] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? scratch[lane] : -INFINITY;
+  return warp_max(t);
+}
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

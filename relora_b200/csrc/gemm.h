@@ -1,0 +1,54 @@
+// Host API of the tcgen05 GEMM family (implemented in gemm_tcgen05.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+// A bf16 matrix operand in global memory.
+//   K-major  (mn_major = false): element (i, k) at ptr[i * ld + k]   (i = row of A / row of B = output column)
+//   MN-major (mn_major = true) : element (i, k) at ptr[k * ld + i]
+struct Operand {
+  const void* ptr = nullptr;
+  long long ld = 0;      // leading dimension in elements (must be a multiple of 8)
+  bool mn_major = false;
+};
+
+// D[M,N] = alpha * ( A1[M,K1] · B1[N,K1]ᵀ  +  A2[M,K2] · B2[N,K2]ᵀ )  (+ residual)  (+ D if accumulate)
+//
+// Grouping (fused LoRA): output columns are split into groups of `n_per_group`; for a tile in group g the
+// K-window of A1 starts at g*a1_group_kofs and the K-window of A2 at g*a2_group_kofs (B rows are the output
+// columns themselves).  With a2_group_kofs = r this evaluates, per group,
+//     y_g = x · W_gᵀ + u_g · B_gᵀ        (u = [u_0 | u_1 | ...] holds the down-projections side by side)
+// in one pass over x and one write of y.
+struct GemmDesc {
+  Operand a1, b1, a2, b2;
+  int M = 0, N = 0, K1 = 0, K2 = 0;
+  int n_per_group = 0;  // 0 => N (single group)
+  int a1_group_kofs = 0, a2_group_kofs = 0;
+  void* out = nullptr;
+  long long ldc = 0;
+  bool out_f32 = false;     // output dtype: bf16 (default) or fp32
+  bool accumulate = false;  // out += result (fp32 outputs: gradient accumulation)
+  const void* residual = nullptr;  // bf16 [M, N], added in fp32 before rounding
+  long long ldr = 0;
+  float alpha = 1.0f;
+  int block_n = 0;  // 0 = auto, else 128 or 256
+  int split_k = 1;  // 1 = off, 0 = auto, >1 = fixed (fp32 accumulate outputs only: partial sums via atomics)
+  // dropout-combine epilogue (backward of the LoRA branch): if n_lora_acc > 0 the A2/B2 products of
+  // the first n_lora_acc K2-windows (each of width lora_r) are kept in separate accumulators and combined as
+  //     out = acc0 + sum_g keep_g(row, col) * acc_{1+g} * inv_keep
+  int n_lora_acc = 0;
+  int lora_r = 0;
+  uint32_t drop_threshold24 = 0;
+  float inv_keep = 1.0f;
+  const uint32_t* seed_ptr = nullptr;  // device: base seed of this step
+  uint32_t seed_key[4] = {0, 0, 0, 0}; // per-accumulator stream keys
+};
+
+void gemm_bf16(const GemmDesc& d, cudaStream_t stream);
+
+// Drop cached TMA descriptors (call when buffers are freed / reallocated).
+void gemm_clear_descriptor_cache();
+
+}  // namespace rb

@@ -1,0 +1,459 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma
+// with fp32 accumulators in tensor memory -> tcgen05.ld epilogue.
+//
+//   D[M,N] = alpha * ( A1[M,K1]·B1[N,K1]ᵀ + A2[M,K2]·B2[N,K2]ᵀ ) (+ residual) (+ D)
+//
+// The second product is the fused LoRA up-projection: it simply extends the K loop ("concat-K"), so the frozen
+// weight GEMM and the low-rank branch share one accumulator, one read of x and one write of y.
+// Reference behaviour being replaced: relora.py:319-322 (F.linear + dropout + two small GEMMs + mul + add).
+//
+// Roles (256 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0   TMA producer      (one elected lane)         smem ring: full[s] / empty[s]
+//   warp 1   MMA issuer        (one elected lane)         tmem ring: tmem_full[a] / tmem_empty[a]
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue         (128 threads == 128 TMEM lanes == 128 rows of the tile)
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "sm100.cuh"
+
+namespace rb {
+
+long long g_launch_count = 0;
+
+using namespace sm100;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+
+struct KernelArgs {
+  int M, N, K1, K2;
+  int n_per_group, a1_group_kofs, a2_group_kofs;
+  void* out;
+  long long ldc;
+  const bf16* residual;
+  long long ldr;
+  float alpha;
+  int out_f32, accumulate;
+  int num_m_tiles, num_n_tiles;
+  int split_k;  // >1: each output tile is computed by split_k CTAs over disjoint K ranges, combined with fp32 atomics
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 128) ? 6 : 4;
+  static constexpr int kTileBytes = kStages * kStageBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;  // +1024 for manual alignment
+};
+
+// Issue the TMA loads of one operand tile (BLOCK_MN x BLOCK_K) into `dst`.
+template <int BLOCK_MN, bool MN_MAJOR>
+__device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int mn0, int k0, uint64_t hint) {
+  if constexpr (!MN_MAJOR) {
+    tma_load_2d(map, bar, dst, k0, mn0, hint);  // box {64 (K), BLOCK_MN}
+  } else {
+#pragma unroll
+    for (int j = 0; j < BLOCK_MN / 64; ++j)  // box {64 (MN), 64 (K)} = 8 KB each
+      tma_load_2d(map, bar, dst + j * 8192, mn0 + j * 64, k0, hint);
+  }
+}
+
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr, int kstep) {
+  if constexpr (!MN_MAJOR) return make_desc_sw128(smem_addr + kstep * (UMMA_K * 2), 16, 1024);
+  return make_desc_sw128(smem_addr + kstep * (UMMA_K * 128), 8192, 1024);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, const KernelArgs p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (256 or 512 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b1);
+    if (p.K2 > 0) {
+      tma_prefetch_desc(&map_a2);
+      tma_prefetch_desc(&map_b2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_work = num_tiles * p.split_k;
+  const int kb1 = (p.K1 + BLOCK_K - 1) / BLOCK_K;
+  const int kb2 = (p.K2 + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = kb1 + kb2;
+  const int kb_per_split = (num_kb + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work / p.split_k, split = work % p.split_k;
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        const int g = n0 / p.n_per_group;
+        const int a1_k = g * p.a1_group_kofs;
+        const int a2_k = g * p.a2_group_kofs;
+        const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (kb < kb1) {
+            load_operand<BLOCK_M, A_MN>(&map_a1, &full_bar[stage], sa, m0, a1_k + kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N, B_MN>(&map_b1, &full_bar[stage], sb, n0, kb * BLOCK_K, kEvictLast);
+          } else {
+            const int k = (kb - kb1) * BLOCK_K;
+            load_operand<BLOCK_M, false>(&map_a2, &full_bar[stage], sa, m0, a2_k + k, kEvictNormal);
+            load_operand<BLOCK_N, false>(&map_b2, &full_bar[stage], sb, n0, k, kEvictLast);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc2 = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work % p.split_k;
+        const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          if (kb < kb1) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc1, ((kb - kb_begin) | k) != 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), idesc2, ((kb - kb_begin) | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================================================================== epilogue (TMEM -> registers -> global)
+    const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        (p.residual == nullptr || (p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.split_k, split = work % p.split_k;
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const bool empty_split = split * kb_per_split >= num_kb;  // nothing was accumulated for this work item
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + c * 32), r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N || empty_split) continue;
+        if (p.split_k > 1) {  // partial sums: fp32 atomics into the (pre-initialised) output
+          float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+          for (int i = 0; i < 32 && col0 + i < p.N; ++i) atomicAdd(op + i, __uint_as_float(r[i]) * p.alpha);
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        const bool full = vec_ok && (col0 + 32 <= p.N);
+        if (p.residual != nullptr) {
+          const bf16* rp = p.residual + (long long)row * p.ldr + col0;
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              bf16x8 t = *reinterpret_cast<const bf16x8*>(rp + q * 8);
+              float f[8];
+              unpack8(t, f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[q * 8 + i] += f[i];
+            }
+          } else {
+            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += __bfloat162float(rp[i]);
+          }
+        }
+        if (p.out_f32) {
+          float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              if (p.accumulate) {
+                float4 old = *reinterpret_cast<float4*>(op + q * 4);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(op + q * 4) = o;
+            }
+          } else {
+            for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = p.accumulate ? op[i] + v[i] : v[i];
+          }
+        } else {
+          bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldc + col0;
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = v[q * 8 + i];
+              if (p.accumulate) {
+                float o[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(op + q * 8), o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += o[i];
+              }
+              *reinterpret_cast<bf16x8*>(op + q * 8) = pack8(f);
+            }
+          } else {
+            for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
+              float o = p.accumulate ? __bfloat162float(op[i]) + v[i] : v[i];
+              op[i] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor-map construction (driver entry point resolved at run time; no link against libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint");
+    if (q != cudaDriverEntryPointSuccess || p == nullptr) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long inner, outer, ld;
+  int box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+void gemm_clear_descriptor_cache() {
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  g_maps.clear();
+}
+
+// 2-D bf16 tensor, `inner` contiguous elements per row, `outer` rows `ld` elements apart, 128B swizzle.
+static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) return it->second;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("gemm operand pointer must be 16-byte aligned");
+  if ((ld * 2) % 16 != 0) throw std::runtime_error("gemm operand leading dimension must be a multiple of 8 elements");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  g_maps.emplace(key, m);
+  return m;
+}
+
+// Operand covering `mn` rows/cols of the output dimension and `k` of the reduction dimension.
+static CUtensorMap operand_map(const Operand& o, long long mn, long long k, int block_mn) {
+  if (!o.mn_major) return make_map_2d(o.ptr, k, mn, o.ld, BLOCK_K, block_mn);
+  return make_map_2d(o.ptr, mn, k, o.ld, 64, BLOCK_K);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static void launch(const GemmDesc& d, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N>;
+  KernelArgs p;
+  p.M = d.M; p.N = d.N; p.K1 = d.K1; p.K2 = d.K2;
+  p.n_per_group = d.n_per_group > 0 ? d.n_per_group : (d.N > 0 ? d.N : 1);
+  p.a1_group_kofs = d.a1_group_kofs; p.a2_group_kofs = d.a2_group_kofs;
+  p.out = d.out; p.ldc = d.ldc; p.residual = reinterpret_cast<const bf16*>(d.residual); p.ldr = d.ldr;
+  p.alpha = d.alpha; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
+  p.num_m_tiles = ceil_div(d.M, BLOCK_M);
+  p.num_n_tiles = ceil_div(d.N, BLOCK_N);
+  const int groups = ceil_div(d.N, p.n_per_group);
+  if (groups > 1 && (p.n_per_group % BLOCK_N) != 0) throw std::runtime_error("gemm: n_per_group must be a multiple of BLOCK_N");
+
+  // K extents of the global tensors include the per-group windows
+  const long long a1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.a1_group_kofs;
+  CUtensorMap ma1 = operand_map(d.a1, d.M, a1_k_total, BLOCK_M);
+  CUtensorMap mb1 = operand_map(d.b1, d.N, d.K1, BLOCK_N);
+  CUtensorMap ma2 = ma1, mb2 = mb1;
+  if (d.K2 > 0) {
+    if (d.a2.mn_major || d.b2.mn_major) throw std::runtime_error("gemm: the LoRA (A2/B2) operands must be K-major");
+    const long long a2_k_total = (long long)d.K2 + (long long)(groups - 1) * d.a2_group_kofs;
+    ma2 = operand_map(d.a2, d.M, a2_k_total, BLOCK_M);
+    mb2 = operand_map(d.b2, d.N, d.K2, BLOCK_N);
+  }
+  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(gemm)");
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = ceil_div(d.K1, BLOCK_K) + ceil_div(d.K2, BLOCK_K);
+  int split = d.split_k;
+  if (split == 0) {  // auto: fill the machine when there are few output tiles and a long reduction
+    split = 1;
+    if (d.out_f32 && d.accumulate && d.residual == nullptr && tiles * 2 <= num_sms() && num_kb >= 16)
+      split = std::min(std::min(num_sms() / tiles, num_kb / 4), 64);
+  }
+  if (split > 1 && !(d.out_f32 && d.accumulate && d.residual == nullptr))
+    throw std::runtime_error("gemm: split_k needs an fp32 accumulate output without residual");
+  if (split < 1) split = 1;
+  // an MMA with no k-blocks would leave the epilogue waiting: every split must own >= 1 k-block or be skipped
+  p.split_k = split;
+  const int work = tiles * split;
+  const int grid = work < num_sms() ? work : num_sms();
+  if (grid <= 0) return;
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, p);
+  RB_CHECK_LAUNCH("gemm_kernel");
+}
+
+template <int BLOCK_N>
+static void dispatch_major(const GemmDesc& d, cudaStream_t s) {
+  if (d.a1.mn_major) {
+    if (d.b1.mn_major) launch<BLOCK_N, true, true>(d, s);
+    else launch<BLOCK_N, true, false>(d, s);
+  } else {
+    if (d.b1.mn_major) launch<BLOCK_N, false, true>(d, s);
+    else launch<BLOCK_N, false, false>(d, s);
+  }
+}
+
+void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
+  if (d.n_lora_acc != 0) throw std::runtime_error("gemm: dropout-combine epilogue not built into this kernel variant");
+  if (d.M <= 0 || d.N <= 0) return;
+  int bn = d.block_n;
+  if (bn == 0) {
+    // wide tiles halve the shared-memory bandwidth per MMA; keep 128 when the group size demands it or N is small
+    const int npg = d.n_per_group > 0 ? d.n_per_group : d.N;
+    bn = (d.N >= 1024 && (npg % 256 == 0 || npg == d.N)) ? 256 : 128;
+  }
+  if (bn == 256) dispatch_major<256>(d, stream);
+  else dispatch_major<128>(d, stream);
+}
+
+}  // namespace rb

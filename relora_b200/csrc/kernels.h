@@ -1,0 +1,69 @@
+// Host API of the bandwidth-bound kernels (elementwise.cu, optim.cu, loss.cu).  All tensors are bf16 unless noted.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+// ---- norms ---------------------------------------------------------------------------------
+// y = w * bf16(x * rstd),  rstd = rsqrt(mean(x^2) + eps).  Optionally also writes G dropout-masked copies
+// xd[m, g*H + k] = keep(seed_g, m, k) ? y[m,k] / (1-p) : 0   (inputs of the LoRA down-projections).
+void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
+                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s);
+// dx = rstd * (g - xhat * mean(g * xhat)) with g = dy * w (+ dx_add);  dw_f32[H] += sum_m dy * bf16(xhat)
+void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw,
+                 int M, int H, cudaStream_t s);
+
+// xd[m, g*H + k] = keep(seed_g, m, k) ? x[m,k] / (1-p) : 0
+void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys,
+                    uint32_t thr24, float inv_keep, cudaStream_t s);
+// out[m,k] = base[m,k] + sum_g keep(seed_g, m, k) * parts[g][m,k] / (1-p)        (backward through the LoRA dropout)
+void dropout_combine(const void* base, const void* parts, long long part_stride, void* out, int M, int H, int G,
+                     const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s);
+
+// ---- rotary --------------------------------------------------------------------------------
+// In-place rotation of the first `n_rot_heads` heads of every row of buf [M, ld] (head h at columns h*hd..),
+// rotary_dim <= hd leading dims of each head; position of row m is (m % T) + pos0.  cos/sin: bf16 [*, rotary_dim].
+void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd, int rotary_dim, const void* cos,
+                  const void* sin, bool backward, int pos0, cudaStream_t s);
+
+// ---- SwiGLU --------------------------------------------------------------------------------
+// gu: [M, 2F] (gate | up) -> h[M, F] = silu(gate) * up
+void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, cudaStream_t s);
+void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,
+                cudaStream_t s);
+
+// ---- embedding -----------------------------------------------------------------------------
+void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int H, cudaStream_t s);
+// dtable_f32[ids[m], :] += dout[m, :]   (skips padding_idx)
+void embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int M, int H, long long padding_idx, cudaStream_t s);
+
+// ---- loss ----------------------------------------------------------------------------------
+// Row-wise softmax cross-entropy over logits [M, ld] (V valid columns), in place:
+//   loss_sum += sum_m nll(m);  count += #valid rows;  logits <- (softmax - onehot) * grad_scale  (0 for ignored rows)
+void cross_entropy_fwd_bwd(void* logits, long long ld, const int64_t* labels, int M, int V, float grad_scale,
+                           long long ignore_index, float* loss_sum, float* count, cudaStream_t s);
+
+// ---- misc ----------------------------------------------------------------------------------
+void transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int R, int C, cudaStream_t s);  // out[C,R]
+void add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t s);
+void cast_f32_to_bf16(const float* in, void* out, long long n, float scale, cudaStream_t s);
+void fill_uniform_hash(void* out, int R, int C, long long ld, uint32_t seed, float bound, cudaStream_t s);  // kaiming re-init
+void seed_advance(uint32_t* seed, cudaStream_t s);  // *seed = lowbias32(*seed + 0x9E3779B9)
+
+// ---- optimizer -----------------------------------------------------------------------------
+// AdamW on flat buffers.  grad may be bf16 or fp32; state bf16 or fp32.  grad_scale / skip are device scalars
+// (may be null => 1 / false).  lr comes from the host (scheduler).
+void adamw_flat(void* param, const void* grad, bool grad_f32, void* exp_avg, void* exp_avg_sq, bool state_f32, long long n,
+                float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale,
+                float grad_scale_host, const float* skip, cudaStream_t s);
+// out[0] += sum(x^2)  (fp32 accumulate; x bf16 or fp32)
+void sumsq(const void* x, bool is_f32, long long n, float* out, cudaStream_t s);
+void random_prune(void* x, bool is_f32, long long n, float ratio, uint32_t seed, long long col_offset, cudaStream_t s);
+// zero every |x| <= thr[0]
+void threshold_prune(void* x, bool is_f32, long long n, const float* thr, cudaStream_t s);
+// magnitude histogram select: thr[0] = approx quantile(|x|, ratio) refined to an exact element value
+void magnitude_quantile(const void* x, bool is_f32, long long n, float ratio, float* thr, void* workspace, cudaStream_t s);
+size_t magnitude_quantile_workspace_bytes();
+
+}  // namespace rb

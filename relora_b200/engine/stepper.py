@@ -74,6 +74,10 @@ class ModuleStepper:
         out = self.model(input_ids=input_ids, labels=input_ids)
         loss = out.loss
         (loss / self.ga).backward()
+        if input_ids.is_cuda:  # fresh LoRA-dropout masks for the next micro-batch (device-side counter)
+            from ..ops import fused
+
+            fused.seed_state.advance(input_ids.device)
         return loss.detach()
 
     @torch.no_grad()

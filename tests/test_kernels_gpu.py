@@ -1,0 +1,408 @@
+"""Numerics of the sm_100a kernels against plain PyTorch fp32 references (run on the B200: -m gpu)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def C():
+    from relora_b200.ops import native
+
+    return native.require()
+
+
+@pytest.fixture(scope="module")
+def F():
+    from relora_b200.ops import fused
+
+    return fused
+
+
+def _rand(*shape, scale=1.0, device="cuda"):
+    return (torch.randn(*shape, device=device, dtype=torch.float32) * scale).to(BF)
+
+
+def _relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp(min=1e-12))
+
+
+# ----------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,block_n", [
+    (128, 128, 64, 128), (256, 256, 128, 128), (384, 768, 768, 128), (1000, 520, 200, 128),
+    (512, 1024, 512, 256), (640, 2304, 768, 256), (130, 264, 72, 0), (2048, 2560, 768, 0),
+])
+def test_gemm_kmajor(F, M, N, K, block_n):
+    torch.manual_seed(0)
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    out = F.gemm(a, b, block_n=block_n)
+    ref = a.float() @ b.float().t()
+    assert out.shape == (M, N)
+    assert _relerr(out, ref) < 6e-3
+
+
+def test_gemm_residual_alpha_accumulate_f32(F):
+    torch.manual_seed(1)
+    M, N, K = 384, 512, 256
+    a, b, r = _rand(M, K), _rand(N, K, scale=0.05), _rand(M, N)
+    out = F.gemm(a, b, residual=r, alpha=0.5)
+    ref = 0.5 * (a.float() @ b.float().t()) + r.float()
+    assert _relerr(out, ref) < 6e-3
+    acc = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    want = acc + a.float() @ b.float().t()
+    F.gemm(a, b, acc, accumulate=True)
+    assert _relerr(acc, want) < 1e-3
+    accb = _rand(M, N)
+    wantb = accb.float() + 2.0 * (a.float() @ b.float().t())
+    F.gemm(a, b, accb, accumulate=True, alpha=2.0)
+    assert _relerr(accb, wantb) < 6e-3
+
+
+@pytest.mark.parametrize("G,Ng,K,r,block_n", [(1, 768, 768, 128, 128), (3, 768, 768, 128, 128), (2, 2560, 768, 128, 256),
+                                               (3, 256, 320, 64, 128), (1, 768, 2560, 128, 256)])
+def test_gemm_fused_lora_groups(F, G, Ng, K, r, block_n):
+    """y_g = x W_gᵀ + u_g B_gᵀ in one launch: the LoRA up-projection as extra K iterations."""
+    torch.manual_seed(2)
+    M, N = 640, G * Ng
+    x, W = _rand(M, K), _rand(N, K, scale=0.03)
+    u, B = _rand(M, G * r), _rand(N, r, scale=0.05)
+    out = F.gemm(x, W, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, block_n=block_n)
+    ref = x.float() @ W.float().t()
+    for g in range(G):
+        ref[:, g * Ng:(g + 1) * Ng] += u[:, g * r:(g + 1) * r].float() @ B[g * Ng:(g + 1) * Ng].float().t()
+    assert _relerr(out, ref) < 6e-3
+
+
+def test_gemm_grouped_a1_window(F):
+    """u_g = xd_g A_gᵀ for G groups at once (per-group K window of A1)."""
+    torch.manual_seed(3)
+    M, K, r, G = 512, 768, 128, 3
+    xd, A = _rand(M, G * K), _rand(G * r, K, scale=0.05)
+    out = F.gemm(xd, A, M=M, N=G * r, K1=K, n_per_group=r, a1_group_kofs=K, alpha=0.25)
+    ref = torch.cat([0.25 * xd[:, g * K:(g + 1) * K].float() @ A[g * r:(g + 1) * r].float().t() for g in range(G)], 1)
+    assert _relerr(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,block_n", [(256, 256, 128, 128), (768, 128, 1024, 128), (384, 512, 320, 256), (200, 136, 96, 128)])
+def test_gemm_mn_major(F, a_mn, b_mn, M, N, K, block_n):
+    torch.manual_seed(4)
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    out = F.gemm(a_in, b_in, M=M, N=N, K1=K, a1_mn=a_mn, b1_mn=b_mn, block_n=block_n)
+    ref = a.float() @ b.float().t()
+    assert _relerr(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("split", [0, 2, 7])
+def test_gemm_split_k_weight_grad(F, split):
+    """dA[r, K] = duᵀ · xd: reduction over tokens, both operands MN-major, fp32 atomics."""
+    torch.manual_seed(5)
+    Mtok, r, K = 4096, 128, 768
+    du, xd = _rand(Mtok, r, scale=0.1), _rand(Mtok, K)
+    out = torch.zeros(r, K, device="cuda", dtype=torch.float32)
+    F.gemm(du, xd, out, M=r, N=K, K1=Mtok, a1_mn=True, b1_mn=True, accumulate=True, split_k=split)
+    ref = du.float().t() @ xd.float()
+    assert _relerr(out, ref) < 2e-3
+
+
+def test_gemm_many_tiles_persistent(F):
+    torch.manual_seed(6)
+    M, N, K = 4096, 2304, 768  # 576 tiles of 128x128 > 148 SMs: exercises the ring phases
+    a, b = _rand(M, K), _rand(N, K, scale=0.03)
+    out = F.gemm(a, b, block_n=128)
+    assert _relerr(out, a.float() @ b.float().t()) < 6e-3
+    out2 = F.gemm(a, b, block_n=256)
+    assert _relerr(out2, a.float() @ b.float().t()) < 6e-3
+
+
+# ----------------------------------------------------------------------------------------- elementwise
+@pytest.mark.parametrize("M,H", [(64, 768), (300, 2048), (17, 4096), (5, 128)])
+def test_rmsnorm_fwd_bwd(C, M, H):
+    from relora_b200.ops import reference as ref
+
+    torch.manual_seed(0)
+    x, w = _rand(M, H), (1 + 0.1 * torch.randn(H, device="cuda")).to(BF)
+    y = torch.empty_like(x)
+    rstd = torch.empty(M, device="cuda", dtype=torch.float32)
+    C.rmsnorm_fwd(x, w, y, rstd, 1e-6, None, None, [], 0.0)
+    want = ref.rmsnorm(x, w, 1e-6)
+    assert _relerr(y, want) < 4e-3
+    # backward vs autograd of the fp32 definition
+    xf, wf = x.float().requires_grad_(), w.float().requires_grad_()
+    dy = _rand(M, H)
+    ref.rmsnorm_fp32(xf, wf, 1e-6).backward(dy.float())
+    dx = torch.empty_like(x)
+    dw = torch.zeros(H, device="cuda", dtype=torch.float32)
+    C.rmsnorm_bwd(dy, x, w, rstd, None, dx, dw)
+    assert _relerr(dx, xf.grad) < 1e-2
+    assert _relerr(dw, wf.grad) < 1e-2
+
+
+def test_dropout_mask_matches_reference_hash(C):
+    from relora_b200.ops import reference as ref
+
+    M, H, p = 96, 256, 0.1
+    x = torch.ones(M, H, device="cuda", dtype=BF)
+    seed = torch.tensor([12345], dtype=torch.int32, device="cuda")
+    keys = [3, 11]
+    xd = torch.empty(M, 2 * H, device="cuda", dtype=BF)
+    C.dropout_expand(x, xd, seed, keys, p)
+    for g, k in enumerate(keys):
+        keep = ref.dropout_keep_mask(ref.mix_seed(12345, k), M, H, p, device="cuda")
+        got = xd.view(M, 2, H)[:, g] != 0
+        assert torch.equal(got, keep)
+        assert abs(float(keep.float().mean()) - 0.9) < 0.02
+    kept_vals = xd[xd != 0].float()
+    assert torch.allclose(kept_vals, torch.full_like(kept_vals, 1 / 0.9), atol=1e-2)
+    # combine = base + mask * part / (1-p)
+    base, part = _rand(M, H), _rand(M, H)
+    out = torch.empty_like(base)
+    C.dropout_combine(base, part.reshape(1, M, H), out, seed, [keys[0]], p)
+    keep = ref.dropout_keep_mask(ref.mix_seed(12345, keys[0]), M, H, p, device="cuda")
+    want = base.float() + keep * part.float() / 0.9
+    assert _relerr(out, want) < 5e-3
+
+
+@pytest.mark.parametrize("hd,rot", [(48, 48), (64, 64), (64, 16), (128, 128)])
+def test_rope_fwd_bwd(C, hd, rot):
+    from relora_b200.ops import reference as ref
+
+    torch.manual_seed(0)
+    B, T, nh = 2, 40, 6
+    buf = _rand(B * T, 3 * nh * hd)
+    cos, sin = ref.rope_tables(rot, 64, device="cuda", dtype=BF)
+    orig = buf.clone()
+    C.rope_inplace(buf, T, 2 * nh, hd, rot, cos, sin, False, 0)
+    x = orig.view(B, T, 3 * nh, hd).float()
+    want = x.clone()
+    want[:, :, : 2 * nh, :rot] = ref.rope_apply(x[:, :, : 2 * nh, :rot].transpose(1, 2), cos[:T].float(), sin[:T].float()).transpose(1, 2)
+    assert _relerr(buf.view(B, T, 3 * nh, hd), want) < 5e-3
+    assert torch.equal(buf.view(B, T, 3 * nh, hd)[:, :, 2 * nh:], orig.view(B, T, 3 * nh, hd)[:, :, 2 * nh:])
+    # backward is the inverse rotation
+    C.rope_inplace(buf, T, 2 * nh, hd, rot, cos, sin, True, 0)
+    assert _relerr(buf, orig) < 1.5e-2
+
+
+def test_swiglu(C):
+    torch.manual_seed(0)
+    M, Fd = 200, 2560
+    gu = _rand(M, 2 * Fd)
+    h = torch.empty(M, Fd, device="cuda", dtype=BF)
+    C.swiglu_fwd(gu, h)
+    g, u = gu[:, :Fd].float().requires_grad_(), gu[:, Fd:].float().requires_grad_()
+    want = torch.nn.functional.silu(g) * u
+    assert _relerr(h, want) < 5e-3
+    dh = _rand(M, Fd)
+    want.backward(dh.float())
+    dgu = torch.empty_like(gu)
+    C.swiglu_bwd(dh, gu, dgu)
+    assert _relerr(dgu[:, :Fd], g.grad) < 6e-3 and _relerr(dgu[:, Fd:], u.grad) < 6e-3
+
+
+def test_embedding(C):
+    torch.manual_seed(0)
+    V, H, M = 1000, 256, 700
+    table = _rand(V, H)
+    ids = torch.randint(0, V, (M,), device="cuda")
+    ids[:5] = V - 1
+    out = torch.empty(M, H, device="cuda", dtype=BF)
+    C.embedding_fwd(ids, table, out)
+    assert torch.equal(out, table[ids])
+    dout = _rand(M, H)
+    dt = torch.zeros(V, H, device="cuda", dtype=torch.float32)
+    C.embedding_bwd(ids, dout, dt, V - 1)
+    want = torch.zeros(V, H, device="cuda").index_add_(0, ids, dout.float())
+    want[V - 1] = 0
+    assert _relerr(dt, want) < 1e-5
+
+
+@pytest.mark.parametrize("V", [32100, 1000, 50257])
+def test_cross_entropy_in_place(C, V):
+    torch.manual_seed(0)
+    M = 64
+    ld = (V + 7) // 8 * 8
+    buf = torch.zeros(M, ld, device="cuda", dtype=BF)
+    logits = buf[:, :V]
+    logits.copy_(_rand(M, V, scale=2.0))
+    labels = torch.randint(0, V, (M,), device="cuda")
+    labels[3] = -100
+    lf = logits.float().clone().requires_grad_()
+    want = torch.nn.functional.cross_entropy(lf, labels, reduction="sum", ignore_index=-100)
+    want.backward()
+    loss, cnt = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    C.cross_entropy_fwd_bwd(logits, labels, V, 1.0, -100, loss, cnt)
+    assert abs(float(loss) - float(want)) / float(want) < 2e-3
+    assert float(cnt) == M - 1
+    assert _relerr(logits, lf.grad) < 1e-2
+    assert float(logits[3].abs().sum()) == 0
+
+
+def test_lm_head_ce_function(F):
+    from relora_b200.ops import reference as ref
+
+    torch.manual_seed(0)
+    B, T, H, V = 3, 65, 256, 32100
+    h = _rand(B, T, H).requires_grad_()
+    w = _rand(V, H, scale=0.05).requires_grad_()
+    labels = torch.randint(0, V, (B, T), device="cuda")
+    loss = F.lm_head_cross_entropy(h, w, labels, chunk=100)
+    loss.backward()
+    hf, wf = h.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    want = ref.lm_head_cross_entropy(hf, wf, labels)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 5e-3
+    assert _relerr(h.grad, hf.grad) < 2e-2
+    assert _relerr(w.grad, wf.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------- optimizer
+@pytest.mark.parametrize("gdt,sdt", [(BF, BF), (torch.float32, BF), (torch.float32, torch.float32)])
+def test_adamw_flat(C, gdt, sdt):
+    from relora_b200.ops import reference as ref
+
+    torch.manual_seed(0)
+    n = 8 * 1000
+    p = _rand(n)
+    g = torch.randn(n, device="cuda").to(gdt)
+    m = (0.1 * torch.randn(n, device="cuda")).to(sdt)
+    v = (0.01 * torch.rand(n, device="cuda")).to(sdt)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    gs = torch.tensor([0.5], device="cuda")
+    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 7, gs, 1.0, None)
+    ref.adamw_step(p2, g, m2, v2, step=7, lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.01, grad_scale=0.5)
+    assert _relerr(p, p2) < 1e-3 and _relerr(m, m2) < 4e-3 and _relerr(v, v2) < 4e-3
+    # device-side skip leaves everything untouched
+    before = p.clone()
+    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 8, None, 1.0, torch.ones(1, device="cuda"))
+    assert torch.equal(before, p)
+
+
+def test_sumsq_and_pruning(C):
+    from relora_b200.ops import reference as ref
+    from relora_b200.relora.optim_reset import magnitude_pruning_
+
+    torch.manual_seed(0)
+    x = _rand(100_003)
+    out = torch.zeros(1, device="cuda")
+    C.sumsq(x, out)
+    assert abs(float(out) - float(x.float().pow(2).sum())) / float(out) < 1e-4
+    # random pruning == reference hash
+    y = torch.ones(50_000, device="cuda", dtype=BF)
+    C.random_prune(y, 0.999, 777, 5)
+    keep = ref.dropout_keep_mask(777, 1, 50_000, 0.999, device="cuda", col_offset=5)[0]
+    assert torch.equal(y != 0, keep)
+    # magnitude pruning == torch.quantile semantics, bf16 and fp32
+    ws = torch.empty(C.quantile_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    thr = torch.zeros(1, device="cuda")
+    for dt in (BF, torch.float32):
+        z = (torch.randn(300_000, device="cuda") * 1e-3).to(dt)
+        want = z.clone()
+        magnitude_pruning_(want, 0.9)
+        C.magnitude_prune(z, 0.9, ws, thr)
+        assert torch.equal(z, want), dt
+
+
+def test_transpose_and_fill(C):
+    from relora_b200.ops import reference as ref
+
+    a = _rand(100, 72)
+    out = torch.empty(72, 100, device="cuda", dtype=BF)
+    C.transpose(a, out)
+    assert torch.equal(out, a.t())
+    w = torch.empty(128, 768, device="cuda", dtype=BF)
+    C.fill_uniform_hash(w, 4242, 1 / math.sqrt(768))
+    want = ref.kaiming_uniform_from_hash(4242, 128, 768, 1 / math.sqrt(768), device="cuda").to(BF)
+    assert torch.equal(w, want)
+    assert float(w.float().abs().max()) <= 1 / math.sqrt(768) + 1e-4
+
+
+# ----------------------------------------------------------------------------------------- module path
+def test_relora_linear_fused_matches_reference():
+    from relora_b200.ops import dispatch
+    from relora_b200.ops import fused
+    from relora_b200.ops import reference as ref
+    from relora_b200.relora import ReLoRaLinear
+
+    torch.manual_seed(0)
+    lin = ReLoRaLinear(768, 2304, r=128, lora_alpha=32, lora_dropout=0.1, bias=False).cuda().to(BF)
+    lin.weight.data.normal_(std=0.02)
+    lin.lora_B.weight.data.normal_(std=0.02)
+    lin.module_index = 4
+    x = _rand(4, 96, 768).requires_grad_()
+    fused.seed_state.set(x.device, 99)
+    lin.train()
+    y = lin(x)
+    dy = _rand(4, 96, 2304, scale=0.1)
+    y.backward(dy)
+    seed = ref.mix_seed(99, 5)
+    xf = x.detach().float().requires_grad_()
+    Af, Bf = lin.lora_A.weight.detach().float().requires_grad_(), lin.lora_B.weight.detach().float().requires_grad_()
+    want = ref.lora_linear(xf, lin.weight.float(), None, Af, Bf, lin.scaling, p=0.1, seed=seed)
+    want.backward(dy.float())
+    assert _relerr(y, want) < 8e-3
+    assert _relerr(x.grad, xf.grad) < 1.5e-2
+    assert _relerr(lin.lora_A.weight.grad, Af.grad) < 1.5e-2
+    assert _relerr(lin.lora_B.weight.grad, Bf.grad) < 1.5e-2
+    # eval: no dropout
+    lin.eval()
+    with torch.no_grad():
+        ye = lin(x)
+    wante = ref.lora_linear(xf.detach(), lin.weight.float(), None, Af.detach(), Bf.detach(), lin.scaling)
+    assert _relerr(ye, wante) < 8e-3
+
+
+def test_merge_kernel_matches_reference():
+    from relora_b200.ops import reference as ref
+    from relora_b200.relora import ReLoRaLinear
+
+    torch.manual_seed(0)
+    lin = ReLoRaLinear(768, 2560, r=128, lora_alpha=32, bias=False).cuda().to(BF)
+    lin.weight.data.normal_(std=0.02)
+    lin.lora_B.weight.data.normal_(std=0.02)
+    want = ref.merge_delta(lin.weight.data, lin.lora_A.weight.data, lin.lora_B.weight.data, lin.scaling)
+    from relora_b200.ops import fused
+
+    assert fused.merge_and_reinit_modules([lin], seed=1, restart_index=2)
+    assert _relerr(lin.weight.data, want) < 3e-3
+    assert float(lin.lora_B.weight.abs().sum()) == 0
+    assert float(lin.lora_A.weight.float().abs().max()) <= 1 / math.sqrt(768) + 1e-4
+
+
+def test_llama_module_path_on_gpu_matches_cpu_reference():
+    """llama_9m-sized model: fused leaf ops on the GPU vs the PyTorch path (same weights)."""
+    import os
+
+    from relora_b200.models import LlamaForCausalLM, load_config
+    from relora_b200.ops import dispatch
+    from relora_b200.relora import ReLoRaModel
+
+    cfg = load_config(os.path.join(os.path.dirname(os.path.dirname(__file__)), "configs", "llama_20m.json"))
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(cfg)
+    w = ReLoRaModel(m, r=64, lora_alpha=32, lora_dropout=0.0, target_modules=["attn", "mlp"], init_lora_a="kaiming")
+    for mod in w.relora_modules():
+        torch.nn.init.normal_(mod.lora_B.weight, std=0.02)
+    w = w.cuda().to(BF)
+    ids = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda")
+    w.train()
+    loss = w(input_ids=ids, labels=ids).loss
+    loss.backward()
+    g_fused = {n: p.grad.float().clone() for n, p in w.named_parameters() if p.grad is not None}
+    w.zero_grad(set_to_none=True)
+    dispatch.force_reference(True)
+    try:
+        loss_ref = w(input_ids=ids, labels=ids).loss
+        loss_ref.backward()
+    finally:
+        dispatch.force_reference(False)
+    assert abs(float(loss) - float(loss_ref)) < 3e-2
+    for n, p in w.named_parameters():
+        if p.grad is not None and ("lora_B" in n or "embed" in n):
+            assert _relerr(g_fused[n], p.grad.float()) < 0.12, n
