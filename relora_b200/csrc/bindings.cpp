@@ -49,7 +49,8 @@ rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
 // out[M,N] = alpha*(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
-          const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k) {
+          const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k, int64_t b1_group_kofs,
+          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup) {
   c10::cuda::CUDAGuard guard(out.device());
   rb::GemmDesc d;
   d.a1 = operand(a1, a1_mn, "a1");
@@ -66,6 +67,8 @@ void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N,
   TORCH_CHECK(out.size(0) >= M && out.size(1) >= N, "out too small");
   d.out = out.data_ptr(); d.ldc = out.stride(0); d.out_f32 = out.scalar_type() == at::kFloat;
   d.accumulate = accumulate; d.alpha = (float)alpha; d.block_n = (int)block_n; d.split_k = (int)split_k;
+  d.b1_group_kofs = (int)b1_group_kofs; d.b1_local_n = b1_local_n; d.m_per_group = (int)m_per_group;
+  d.b1_mn_ofs_per_mgroup = (int)b1_mn_ofs_per_mgroup;
   if (residual.has_value()) {
     chk_bf16(*residual, "residual");
     chk_2d_rowmajor(*residual, "residual");
@@ -125,16 +128,25 @@ void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vec
 }
 
 void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, const OptTensor& seed, std::vector<int64_t> keys, double p) {
+  // parts: either [G, M, H] contiguous, or [M, G*H] row-major (group g at column offset g*H)
   chk_bf16(parts, "parts"); chk_bf16(out, "out");
-  TORCH_CHECK(parts.dim() == 3 && parts.is_contiguous() && out.is_contiguous(), "parts must be contiguous [G, M, H]");
-  const int G = (int)parts.size(0), M = (int)parts.size(1), H = (int)parts.size(2);
-  TORCH_CHECK((int)keys.size() == G && out.numel() == (int64_t)M * H);
+  TORCH_CHECK(out.dim() == 2 && out.is_contiguous(), "out must be contiguous [M, H]");
+  const int M = (int)out.size(0), H = (int)out.size(1);
+  const int G = (int)keys.size();
+  long long part_stride, ld_parts;
+  if (parts.dim() == 3) {
+    TORCH_CHECK(parts.is_contiguous() && parts.size(0) == G && parts.size(1) == M && parts.size(2) == H, "parts must be [G, M, H]");
+    part_stride = (long long)M * H; ld_parts = H;
+  } else {
+    TORCH_CHECK(parts.dim() == 2 && parts.stride(1) == 1 && parts.size(0) == M && parts.size(1) == (int64_t)G * H, "parts must be [M, G*H]");
+    part_stride = H; ld_parts = parts.stride(0);
+  }
   uint32_t k[4] = {0, 0, 0, 0};
   for (int i = 0; i < G && i < 4; ++i) k[i] = (uint32_t)keys[i];
   const void* bp = nullptr;
-  if (base.has_value()) { chk_bf16(*base, "base"); TORCH_CHECK(base->is_contiguous()); bp = base->data_ptr(); }
+  if (base.has_value()) { chk_bf16(*base, "base"); TORCH_CHECK(base->is_contiguous() && base->numel() == out.numel()); bp = base->data_ptr(); }
   c10::cuda::CUDAGuard guard(out.device());
-  rb::dropout_combine(bp, parts.data_ptr(), (long long)M * H, out.data_ptr(), M, H, G, u32ptr(seed), k,
+  rb::dropout_combine(bp, parts.data_ptr(), part_stride, ld_parts, out.data_ptr(), M, H, G, u32ptr(seed), k,
                       (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 

@@ -186,7 +186,8 @@ void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t
 }
 
 __global__ void __launch_bounds__(256) dropout_combine_kernel(const bf16* __restrict__ basep, const bf16* __restrict__ parts,
-                                                              long long part_stride, bf16* __restrict__ out, long long n_vec, int H, int G,
+                                                              long long part_stride, long long ld_parts, bf16* __restrict__ out,
+                                                              long long n_vec, int H, int G,
                                                               const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr24,
                                                               float inv_keep) {
   const uint32_t base = seed_ptr ? *seed_ptr : 0u;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) dropout_combine_kernel(const bf16* __rest
     }
     for (int g = 0; g < G; ++g) {
       float f[8];
-      unpack8(reinterpret_cast<const bf16x8*>(parts + g * part_stride)[i], f);
+      unpack8(*reinterpret_cast<const bf16x8*>(parts + g * part_stride + row * ld_parts + c * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24)) acc[j] += f[j] * inv_keep;
@@ -212,13 +213,13 @@ __global__ void __launch_bounds__(256) dropout_combine_kernel(const bf16* __rest
   }
 }
 
-void dropout_combine(const void* base, const void* parts, long long part_stride, void* out, int M, int H, int G,
+void dropout_combine(const void* base, const void* parts, long long part_stride, long long ld_parts, void* out, int M, int H, int G,
                      const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s) {
   if (H % 8 != 0 || G < 1 || G > 4) throw std::runtime_error("dropout_combine: bad shape");
   uint4 k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
   const long long n_vec = (long long)M * H / 8;
   const int grid = (int)std::min<long long>((n_vec + 255) / 256, (long long)num_sms() * 8);
-  dropout_combine_kernel<<<grid, 256, 0, s>>>((const bf16*)base, (const bf16*)parts, part_stride, (bf16*)out, n_vec, H, G, seed_ptr, k,
+  dropout_combine_kernel<<<grid, 256, 0, s>>>((const bf16*)base, (const bf16*)parts, part_stride, ld_parts, (bf16*)out, n_vec, H, G, seed_ptr, k,
                                               thr24, inv_keep);
   RB_CHECK_LAUNCH("dropout_combine");
 }

@@ -26,6 +26,11 @@ struct GemmDesc {
   int M = 0, N = 0, K1 = 0, K2 = 0;
   int n_per_group = 0;  // 0 => N (single group)
   int a1_group_kofs = 0, a2_group_kofs = 0;
+  // B1 addressing for the backward GEMMs: K-window offset per N-group, MN coordinate taken relative to the group,
+  // and an extra MN offset chosen by the group of the M-tile (stacked weight-gradient GEMMs dA_cat / dB_cat).
+  int b1_group_kofs = 0;
+  bool b1_local_n = false;
+  int m_per_group = 0, b1_mn_ofs_per_mgroup = 0;
   void* out = nullptr;
   long long ldc = 0;
   bool out_f32 = false;     // output dtype: bf16 (default) or fp32

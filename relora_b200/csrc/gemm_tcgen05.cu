@@ -37,6 +37,8 @@ constexpr int kEpilogueWarp0 = 4;
 struct KernelArgs {
   int M, N, K1, K2;
   int n_per_group, a1_group_kofs, a2_group_kofs;
+  int b1_group_kofs, b1_local_n;        // B1: K-window offset per N-group; MN coordinate relative to the group
+  int m_per_group, b1_mn_ofs_per_mgroup; // B1: extra MN offset selected by the M-tile's group (weight gradients)
   void* out;
   long long ldc;
   const bf16* residual;
@@ -142,6 +144,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         const int g = n0 / p.n_per_group;
         const int a1_k = g * p.a1_group_kofs;
         const int a2_k = g * p.a2_group_kofs;
+        const int b1_k = g * p.b1_group_kofs;
+        const int b1_n = (p.b1_local_n ? n0 - g * p.n_per_group : n0) + (m0 / p.m_per_group) * p.b1_mn_ofs_per_mgroup;
         const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -150,7 +154,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           if (kb < kb1) {
             load_operand<BLOCK_M, A_MN>(&map_a1, &full_bar[stage], sa, m0, a1_k + kb * BLOCK_K, kEvictNormal);
-            load_operand<BLOCK_N, B_MN>(&map_b1, &full_bar[stage], sb, n0, kb * BLOCK_K, kEvictLast);
+            load_operand<BLOCK_N, B_MN>(&map_b1, &full_bar[stage], sb, b1_n, b1_k + kb * BLOCK_K, kEvictLast);
           } else {
             const int k = (kb - kb1) * BLOCK_K;
             load_operand<BLOCK_M, false>(&map_a2, &full_bar[stage], sa, m0, a2_k + k, kEvictNormal);
@@ -388,6 +392,8 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   p.M = d.M; p.N = d.N; p.K1 = d.K1; p.K2 = d.K2;
   p.n_per_group = d.n_per_group > 0 ? d.n_per_group : (d.N > 0 ? d.N : 1);
   p.a1_group_kofs = d.a1_group_kofs; p.a2_group_kofs = d.a2_group_kofs;
+  p.b1_group_kofs = d.b1_group_kofs; p.b1_local_n = d.b1_local_n ? 1 : 0;
+  p.m_per_group = d.m_per_group > 0 ? d.m_per_group : (1 << 30); p.b1_mn_ofs_per_mgroup = d.b1_mn_ofs_per_mgroup;
   p.out = d.out; p.ldc = d.ldc; p.residual = reinterpret_cast<const bf16*>(d.residual); p.ldr = d.ldr;
   p.alpha = d.alpha; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
   p.num_m_tiles = ceil_div(d.M, BLOCK_M);
@@ -398,7 +404,11 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   // K extents of the global tensors include the per-group windows
   const long long a1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.a1_group_kofs;
   CUtensorMap ma1 = operand_map(d.a1, d.M, a1_k_total, BLOCK_M);
-  CUtensorMap mb1 = operand_map(d.b1, d.N, d.K1, BLOCK_N);
+  const int mgroups = d.m_per_group > 0 ? ceil_div(d.M, d.m_per_group) : 1;
+  const long long b1_mn_total = (d.b1_local_n ? (long long)p.n_per_group : (long long)d.N) + (long long)(mgroups - 1) * d.b1_mn_ofs_per_mgroup;
+  const long long b1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.b1_group_kofs;
+  if (d.m_per_group > 0 && (d.m_per_group % BLOCK_M) != 0) throw std::runtime_error("gemm: m_per_group must be a multiple of 128");
+  CUtensorMap mb1 = operand_map(d.b1, b1_mn_total, b1_k_total, BLOCK_N);
   CUtensorMap ma2 = ma1, mb2 = mb1;
   if (d.K2 > 0) {
     if (d.a2.mn_major || d.b2.mn_major) throw std::runtime_error("gemm: the LoRA (A2/B2) operands must be K-major");

@@ -17,8 +17,9 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
 // xd[m, g*H + k] = keep(seed_g, m, k) ? x[m,k] / (1-p) : 0
 void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys,
                     uint32_t thr24, float inv_keep, cudaStream_t s);
-// out[m,k] = base[m,k] + sum_g keep(seed_g, m, k) * parts[g][m,k] / (1-p)        (backward through the LoRA dropout)
-void dropout_combine(const void* base, const void* parts, long long part_stride, void* out, int M, int H, int G,
+// out[m,k] = base[m,k] + sum_g keep(seed_g, m, k) * part_g[m,k] / (1-p)        (backward through the LoRA dropout)
+// part_g[m,k] = parts[g*part_stride + m*ld_parts + k]
+void dropout_combine(const void* base, const void* parts, long long part_stride, long long ld_parts, void* out, int M, int H, int G,
                      const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s);
 
 // ---- rotary --------------------------------------------------------------------------------

@@ -79,6 +79,10 @@ def gemm(
     out_dtype: torch.dtype = _BF16,
     block_n: int = 0,
     split_k: int = 1,
+    b1_group_kofs: int = 0,
+    b1_local_n: bool = False,
+    m_per_group: int = 0,
+    b1_mn_ofs_per_mgroup: int = 0,
 ) -> torch.Tensor:
     """``out[M,N] = alpha·(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)`` on the tcgen05 kernel.
 
@@ -99,7 +103,8 @@ def gemm(
         out = buf[:, :N] if ld != N else buf
         assert not accumulate
     _C().gemm(a1, b1, out, M, N, K1, a2, b2, K2, a1_mn, b1_mn, n_per_group, a1_group_kofs, a2_group_kofs,
-              residual, float(alpha), accumulate, block_n, split_k)
+              residual, float(alpha), accumulate, block_n, split_k, b1_group_kofs, b1_local_n, m_per_group,
+              b1_mn_ofs_per_mgroup)
     return out
 
 
