@@ -178,7 +178,10 @@ def run_ours(args):
 
     for i in range(args.warmup):
         eng.train_step_device(dev_tokens[i])
-    C.reset_launch_count()
+    if hasattr(eng.stepper, "mark_launch_window"):
+        eng.stepper.mark_launch_window()
+    else:
+        C.reset_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()

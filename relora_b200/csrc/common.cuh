@@ -97,21 +97,26 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
   return warp_max(t);
 }
 
-struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
-};
+// 8 packed bf16 moved as one 128-bit access.  (A struct of four bfloat162 is copied member-wise by nvcc, which
+// turns every load/store into four 32-bit transactions; the builtin vector type keeps LDG/STG.128.)
+typedef uint4 bf16x8;
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+  const uint32_t w[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
+    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    float2 t = __bfloat1622float2(b);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
-  bf16x8 p;
+  uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return p;
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

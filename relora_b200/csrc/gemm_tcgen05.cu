@@ -46,6 +46,7 @@ struct KernelArgs {
   float alpha;
   int out_f32, accumulate;
   int num_m_tiles, num_n_tiles;
+  int use_tma_store;  // bf16 output written through swizzled smem slabs + TMA store
   int split_k;  // >1: each output tile is computed by split_k CTAs over disjoint K ranges, combined with fp32 atomics
 };
 
@@ -54,10 +55,11 @@ struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 128) ? 6 : 4;
+  static constexpr int kStages = (BLOCK_N == 128) ? 5 : 3;
   static constexpr int kTileBytes = kStages * kStageBytes;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;  // +1024 for manual alignment
+  static constexpr int kBarrierBytes = 1024;                          // barriers + tmem slot (keeps the slabs 1024-aligned)
+  static constexpr int kSlabBytes = BLOCK_M * 128;                    // one 128 x 64 bf16 output slab (128B swizzle)
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + 2 * kSlabBytes + 1024;  // +1024 for manual alignment
 };
 
 // Issue the TMA loads of one operand tile (BLOCK_MN x BLOCK_K) into `dst`.
@@ -81,7 +83,8 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr, int kstep) 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
-            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, const KernelArgs p) {
+            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+            const __grid_constant__ CUtensorMap map_out, const KernelArgs p) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (256 or 512 columns)
@@ -104,6 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       tma_prefetch_desc(&map_a2);
       tma_prefetch_desc(&map_b2);
     }
+    if (p.use_tma_store) tma_prefetch_desc(&map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -210,12 +214,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       }
     }
   } else if (warp >= kEpilogueWarp0) {
-    // ===================================================================== epilogue (TMEM -> registers -> global)
-    const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue
+    // TMEM -> registers (two 32-column loads in flight) -> fp32 math -> either
+    //   (a) bf16, 128B-swizzled shared-memory slab -> TMA store (full-line, asynchronous, clips ragged edges), or
+    //   (b) direct 128-bit global accesses (fp32 outputs, accumulation, split-K atomics).
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const uint32_t et = threadIdx.x - kEpilogueWarp0 * 32;  // 0..127 == row inside the tile
+    const bool issuer = (et == 0);
+    uint8_t* stage_base = smem + L::kTileBytes + L::kBarrierBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                        (p.residual == nullptr || (p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
+    const bool res_vec = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const bool out_vec = (p.ldc % (p.out_f32 ? 4 : 8) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    int slab_counter = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int tile = work / p.split_k, split = work % p.split_k;
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
@@ -226,82 +237,134 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + c * 32), r);
+      for (int sl = 0; sl < BLOCK_N / 64; ++sl) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64), r0);
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64 + 32), r1);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N || empty_split) continue;
-        if (p.split_k > 1) {  // partial sums: fp32 atomics into the (pre-initialised) output
-          float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
-          for (int i = 0; i < 32 && col0 + i < p.N; ++i) atomicAdd(op + i, __uint_as_float(r[i]) * p.alpha);
-          continue;
+        if (sl == BLOCK_N / 64 - 1) {  // accumulator fully read: hand it back to the MMA warp early
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
         }
-        float v[32];
+        const int col0 = n0 + sl * 64;
+        if (p.use_tma_store) {
+          // ---- (a) bf16 via swizzled smem + TMA store
+          uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
+          if (issuer) tma_store_wait_read<1>();  // the store that used this slab two slabs ago has drained
+          named_bar_sync(1, 128);
+          uint4 packed[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        const bool full = vec_ok && (col0 + 32 <= p.N);
-        if (p.residual != nullptr) {
-          const bf16* rp = p.residual + (long long)row * p.ldr + col0;
-          if (full) {
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              bf16x8 t = *reinterpret_cast<const bf16x8*>(rp + q * 8);
-              float f[8];
-              unpack8(t, f);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+              f[i] = __uint_as_float(raw) * p.alpha;
+            }
+            if (p.residual != nullptr && row_ok) {
+              const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
+              if (res_vec && col0 + q * 8 + 8 <= p.N) {
+                float a[8];
+                unpack8(*reinterpret_cast<const uint4*>(rp), a);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[q * 8 + i] += f[i];
+                for (int i = 0; i < 8; ++i) f[i] += a[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (col0 + q * 8 + i < p.N) f[i] += __bfloat162float(rp[i]);
+              }
+            }
+            packed[q] = pack8(f);
+          }
+          const uint32_t rloc = quad * 32 + lane;
+          uint8_t* rowp = slab + rloc * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer && !empty_split) {
+            tma_store_2d(&map_out, slab, col0, m0);
+            tma_store_commit();
+          }
+          ++slab_counter;
+        } else if (row_ok && !empty_split && col0 < p.N) {
+          // ---- (b) direct global path
+          if (p.split_k > 1) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              const uint32_t raw = (i < 32) ? r0[i] : r1[i - 32];
+              if (col0 + i < p.N) atomicAdd(op + i, __uint_as_float(raw) * p.alpha);
+            }
+          } else if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float4 o;
+              o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
+              o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
+              o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
+              o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              if (out_vec && col0 + q * 4 + 4 <= p.N) {
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(op + q * 4);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(op + q * 4) = o;
+              } else {
+                const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col0 + q * 4 + i < p.N) op[q * 4 + i] = p.accumulate ? op[q * 4 + i] + e[i] : e[i];
+              }
             }
           } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += __bfloat162float(rp[i]);
-          }
-        }
-        if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
-          if (full) {
+            bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              if (p.accumulate) {
-                float4 old = *reinterpret_cast<float4*>(op + q * 4);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(op + q * 4) = o;
-            }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = p.accumulate ? op[i] + v[i] : v[i];
-          }
-        } else {
-          bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = v[q * 8 + i];
-              if (p.accumulate) {
-                float o[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(op + q * 8), o);
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(q < 4 ? r0[q * 8 + i] : r1[(q - 4) * 8 + i]) * p.alpha;
+              const bool fullv = col0 + q * 8 + 8 <= p.N;
+              if (p.residual != nullptr) {
+                const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
+                if (res_vec && fullv) {
+                  float a[8];
+                  unpack8(*reinterpret_cast<const uint4*>(rp), a);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += o[i];
+                  for (int i = 0; i < 8; ++i) f[i] += a[i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (col0 + q * 8 + i < p.N) f[i] += __bfloat162float(rp[i]);
+                }
               }
-              *reinterpret_cast<bf16x8*>(op + q * 8) = pack8(f);
-            }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
-              float o = p.accumulate ? __bfloat162float(op[i]) + v[i] : v[i];
-              op[i] = __float2bfloat16_rn(o);
+              if (out_vec && fullv) {
+                if (p.accumulate) {
+                  float a[8];
+                  unpack8(*reinterpret_cast<const uint4*>(op + q * 8), a);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += a[i];
+                }
+                *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (col0 + q * 8 + i < p.N) {
+                    const float o = p.accumulate ? __bfloat162float(op[q * 8 + i]) + f[i] : f[i];
+                    op[q * 8 + i] = __float2bfloat16_rn(o);
+                  }
+              }
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (p.use_tma_store && issuer) tma_store_wait<0>();  // all output bytes are globally visible before exit
   }
 
   tc_fence_before();
@@ -438,7 +501,11 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   const int work = tiles * split;
   const int grid = work < num_sms() ? work : num_sms();
   if (grid <= 0) return;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, p);
+  p.use_tma_store = (!d.out_f32 && !d.accumulate && split == 1 && (d.ldc % 8 == 0) &&
+                     (reinterpret_cast<uintptr_t>(d.out) & 15) == 0) ? 1 : 0;
+  CUtensorMap mout = ma1;
+  if (p.use_tma_store) mout = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, p);
   RB_CHECK_LAUNCH("gemm_kernel");
 }
 

@@ -1,12 +1,503 @@
-"""Whole-layer fused Llama + ReLoRA executor for B200 (stacked QKV / gate-up weights, LoRA folded into
-the tcgen05 GEMMs, flat fp32 gradient accumulation, CUDA-graph captured micro-steps)."""
+"""Whole-model fused executor for Llama + ReLoRA on B200.
+
+The reference executes one ``ReLoRaLinear`` as ~8 eager kernels (``relora.py:319-322``) and a decoder
+layer as ~100 (``modeling_llama.py:243-308``), re-reading every activation several times, and is
+launch/CPU-bound at the 250M scale.  This executor instead
+
+* keeps the frozen weights of a layer *stacked* (``Wqkv [3h,h]``, ``Wgu [2f,h]``) and the LoRA factors
+  stacked alongside (``A_qkv [3r,h]``, ``B_qkv [3h,r]`` …) — the ``nn.Module`` parameters are views into these
+  buffers, so checkpoints keep the reference layout;
+* runs every projection as ONE tcgen05 GEMM launch with the low-rank up-projection folded into the K loop
+  (``y = [x | u]·[W | B]ᵀ``, residual add in the epilogue), the three / two down-projections of a stacked group
+  as one grouped launch, and all backward GEMMs (``dx``, ``du``, stacked ``dA`` / ``dB`` with split-K) on the same
+  kernel reading operands MN-major in place — no transposed copies, no autograd graph;
+* fuses RMSNorm with the LoRA-dropout expansion, computes LM-head + cross-entropy chunk-wise without ever
+  materialising ``[tokens, V]`` logits, accumulates all gradients in one flat fp32 buffer;
+* captures forward+backward of a micro-batch in a CUDA graph (dropout seeds live on the device and advance
+  inside the graph), so a micro-step costs one graph launch on the host.
+
+Math per layer (training, dropout p, scale s): see ``ops/reference.py`` — numerics tests compare this executor
+with the module-by-module PyTorch path on identical weights and masks.
+"""
 from __future__ import annotations
 
+import math
+from typing import Dict, List, Optional, Tuple
 
-def supports(model, args):
-    return False, "fused executor not built yet"
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F_
+
+from ..models.llama import LlamaForCausalLM
+from ..ops import fused, native
+from ..parallel.dist import DistInfo
+from ..parallel.flat import FlatAdamW, FlatParamStore
+from ..parallel.grad_sync import GradSync, broadcast_params
+from ..relora import ReLoRaLinear, ReLoRaModel
+from .stepper import UpdateInfo
+
+BF = torch.bfloat16
 
 
-class FusedLlamaStepper:  # pragma: no cover - placeholder until the executor lands
-    def __init__(self, *a, **k):
-        raise NotImplementedError
+def supports(model, args=None) -> Tuple[bool, str]:
+    if not isinstance(model, ReLoRaModel):
+        return False, "full-rank training uses the module path"
+    inner = model.wrapped_model
+    if not isinstance(inner, LlamaForCausalLM):
+        return False, "only Llama is fused"
+    if model.lora_only or model.trainable_scaling or model._config.quantize is not None:
+        return False, "lora_only / trainable scaling / quantized frozen weights use the module path"
+    cfg = inner.config
+    h, f, nh = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+    r = model.r
+    hd = h // nh
+    if h % 128 or f % 128 or r % 128:
+        return False, f"hidden ({h}), intermediate ({f}) and rank ({r}) must be multiples of 128 for stacked groups"
+    if hd % 8 or hd % 4:
+        return False, "head_dim must be a multiple of 8"
+    p = next(inner.parameters())
+    if not p.is_cuda or p.dtype != BF:
+        return False, "needs CUDA + bfloat16"
+    for m in inner.modules():
+        if isinstance(m, ReLoRaLinear) and m.bias is not None:
+            return False, "biased projections use the module path"
+    return True, "ok"
+
+
+class _Layer:
+    """Stacked views of one decoder layer's parameters and gradients."""
+
+    __slots__ = ("Wqkv", "Wo", "Wgu", "Wd", "A_qkv", "B_qkv", "A_o", "B_o", "A_gu", "B_gu", "A_d", "B_d", "w1", "w2",
+                 "gA_qkv", "gB_qkv", "gA_o", "gB_o", "gA_gu", "gB_gu", "gA_d", "gB_d", "gw1", "gw2", "keys_qkv", "key_o",
+                 "keys_gu", "key_d", "mods")
+
+
+class FusedLlamaStepper:
+    def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
+                 transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096):
+        ok, why = supports(model)
+        if not ok:
+            raise RuntimeError(why)
+        self.model, self.info = model, info
+        self.inner: LlamaForCausalLM = model.wrapped_model
+        self.C = fused._C()
+        self.ga = grad_accumulation
+        self.clip = clip_grad_norm
+        self.use_graphs = cuda_graphs
+        self.ce_chunk = ce_chunk
+        cfg = self.inner.config
+        self.h, self.f, self.nh, self.V = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.vocab_size
+        self.hd = self.h // self.nh
+        self.r = model.r
+        self.L = cfg.num_hidden_layers
+        self.eps = cfg.rms_norm_eps
+        self.p = float(model.lora_dropout)
+        self.scale = float(model.lora_alpha) / model.r
+        self.device = info.device
+        broadcast_params(model)
+
+        # ---------------------------------------------------------------- stacked frozen weights
+        dev = self.device
+        h, f, r, L = self.h, self.f, self.r, self.L
+        self.Wqkv = torch.empty(L, 3 * h, h, dtype=BF, device=dev)
+        self.Wo = torch.empty(L, h, h, dtype=BF, device=dev)
+        self.Wgu = torch.empty(L, 2 * f, h, dtype=BF, device=dev)
+        self.Wd = torch.empty(L, h, f, dtype=BF, device=dev)
+        layers = self.inner.model.layers
+        with torch.no_grad():
+            for l, layer in enumerate(layers):
+                at, mlp = layer.self_attn, layer.mlp
+                for j, m in enumerate((at.q_proj, at.k_proj, at.v_proj)):
+                    self._rehome(m.weight, self.Wqkv[l, j * h:(j + 1) * h])
+                self._rehome(at.o_proj.weight, self.Wo[l])
+                self._rehome(mlp.gate_proj.weight, self.Wgu[l, :f])
+                self._rehome(mlp.up_proj.weight, self.Wgu[l, f:])
+                self._rehome(mlp.down_proj.weight, self.Wd[l])
+
+        # ---------------------------------------------------------------- flat trainable store (stack-friendly order)
+        named: List[Tuple[str, torch.nn.Parameter]] = []
+        name_of = {id(p): n for n, p in model.named_parameters()}
+
+        def add(p):
+            named.append((name_of[id(p)], p))
+
+        for layer in layers:
+            at, mlp = layer.self_attn, layer.mlp
+            for m in (at.q_proj, at.k_proj, at.v_proj):
+                add(m.lora_A.weight)
+            for m in (at.q_proj, at.k_proj, at.v_proj):
+                add(m.lora_B.weight)
+            add(at.o_proj.lora_A.weight); add(at.o_proj.lora_B.weight)
+            add(mlp.gate_proj.lora_A.weight); add(mlp.up_proj.lora_A.weight)
+            add(mlp.gate_proj.lora_B.weight); add(mlp.up_proj.lora_B.weight)
+            add(mlp.down_proj.lora_A.weight); add(mlp.down_proj.lora_B.weight)
+            add(layer.input_layernorm.weight); add(layer.post_attention_layernorm.weight)
+        add(self.inner.model.embed_tokens.weight)
+        add(self.inner.model.norm.weight)
+        add(self.inner.lm_head.weight)
+        seen = {id(p) for _, p in named}
+        extra = [(n, p) for n, p in model.named_parameters() if p.requires_grad and id(p) not in seen]
+        if extra:
+            raise RuntimeError(f"unexpected trainable parameters for the fused executor: {[n for n, _ in extra]}")
+        self.store = FlatParamStore(named, world_size=info.world_size, grad_dtype=torch.float32, bind_grads=False)
+        self.trainable_params = [p for _, p in named]
+        self.trainable_names = [n for n, _ in named]
+        self.lora_params = [p for n, p in named if "lora_" in n]
+
+        def pv(p, rows_mult=1):  # stacked view over `rows_mult` adjacent parameters (params and grads)
+            o, n = self.store.segment(p)
+            shape = (p.shape[0] * rows_mult, p.shape[1]) if p.dim() == 2 else (p.shape[0] * rows_mult,)
+            tot = n * rows_mult
+            return self.store.params[o:o + tot].view(shape), self.store.grads[o:o + tot].view(shape)
+
+        self.layers: List[_Layer] = []
+        for layer in layers:
+            at, mlp = layer.self_attn, layer.mlp
+            S = _Layer()
+            l = len(self.layers)
+            S.Wqkv, S.Wo, S.Wgu, S.Wd = self.Wqkv[l], self.Wo[l], self.Wgu[l], self.Wd[l]
+            S.A_qkv, S.gA_qkv = pv(at.q_proj.lora_A.weight, 3)
+            S.B_qkv, S.gB_qkv = pv(at.q_proj.lora_B.weight, 3)
+            S.A_o, S.gA_o = pv(at.o_proj.lora_A.weight)
+            S.B_o, S.gB_o = pv(at.o_proj.lora_B.weight)
+            S.A_gu, S.gA_gu = pv(mlp.gate_proj.lora_A.weight, 2)
+            S.B_gu, S.gB_gu = pv(mlp.gate_proj.lora_B.weight, 2)
+            S.A_d, S.gA_d = pv(mlp.down_proj.lora_A.weight)
+            S.B_d, S.gB_d = pv(mlp.down_proj.lora_B.weight)
+            S.w1, S.gw1 = pv(layer.input_layernorm.weight)
+            S.w2, S.gw2 = pv(layer.post_attention_layernorm.weight)
+            S.keys_qkv = [m.module_index + 1 for m in (at.q_proj, at.k_proj, at.v_proj)]
+            S.key_o = at.o_proj.module_index + 1
+            S.keys_gu = [mlp.gate_proj.module_index + 1, mlp.up_proj.module_index + 1]
+            S.key_d = mlp.down_proj.module_index + 1
+            S.mods = (at.q_proj, at.k_proj, at.v_proj, at.o_proj, mlp.gate_proj, mlp.up_proj, mlp.down_proj)
+            # sanity: the stacked views must alias the module parameters
+            assert S.A_qkv[r:2 * r].data_ptr() == at.k_proj.lora_A.weight.data_ptr()
+            assert S.B_gu[f:].data_ptr() == mlp.up_proj.lora_B.weight.data_ptr()
+            self.layers.append(S)
+        emb = self.inner.model.embed_tokens
+        self.W_emb, self.gW_emb = pv(emb.weight)
+        self.pad_idx = emb.padding_idx if emb.padding_idx is not None else -1
+        self.w_norm, self.gw_norm = pv(self.inner.model.norm.weight)
+        self.W_head, self.gW_head = pv(self.inner.lm_head.weight)
+
+        rot = layers[0].self_attn.rotary_emb
+        self.cos = rot.cos_cached[0, 0].to(BF).contiguous()
+        self.sin = rot.sin_cached[0, 0].to(BF).contiguous()
+
+        # ---------------------------------------------------------------- optimizer / comm
+        symm = symm_factory.bind(self.store) if (symm_factory is not None and transport == "p2p") else None
+        self.sync = GradSync(self.store, info, transport=transport, zero=zero, symm=symm)
+        shard = self.sync.shard if zero else None
+        self.optimizer = FlatAdamW(self.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, shard=shard,
+                                   native=native or fused.NativeOptim())
+        self.seed = fused.seed_state.get(dev)
+        self._shape = None
+        self._graph = None
+        self._replays = 0
+        self._launches_per_micro = 0
+        self._attn_saved: List = []
+
+    # ------------------------------------------------------------------ plumbing
+    @staticmethod
+    def _rehome(param: torch.nn.Parameter, dst: torch.Tensor):
+        dst.copy_(param.data)
+        param.data = dst
+
+    def _alloc(self, B: int, T: int):
+        dev, h, f, r, L = self.device, self.h, self.f, self.r, self.L
+        M = B * T
+        e = lambda *s: torch.empty(*s, dtype=BF, device=dev)  # noqa: E731
+        self.B_, self.T_, self.M_ = B, T, M
+        self.ids = torch.zeros(B, T, dtype=torch.long, device=dev)
+        self.labels = torch.zeros(M, dtype=torch.long, device=dev)
+        self.x_in = e(L + 1, M, h)
+        self.x1 = e(L, M, h)
+        self.rstd1 = torch.empty(L, M, dtype=torch.float32, device=dev)
+        self.rstd2 = torch.empty(L, M, dtype=torch.float32, device=dev)
+        self.rstd_f = torch.empty(M, dtype=torch.float32, device=dev)
+        G3, G2 = (3, 2) if self.p > 0 else (1, 1)
+        self.xd_qkv = e(L, M, G3 * h)
+        self.xd_o = e(L, M, h)
+        self.xd_gu = e(L, M, G2 * h)
+        self.xd_d = e(L, M, f)
+        self.u_qkv = e(L, M, 3 * r)
+        self.u_o = e(L, M, r)
+        self.u_gu = e(L, M, 2 * r)
+        self.u_d = e(L, M, r)
+        self.qkv = e(L, M, 3 * h)
+        self.gu = e(L, M, 2 * f)
+        # transients
+        self.xn = e(M, h)
+        self.hmid = e(M, f)
+        self.xf = e(M, h)
+        self.dxf = e(M, h)
+        self.dx_a, self.dx_b, self.dxn, self.dxn2 = e(M, h), e(M, h), e(M, h), e(M, h)
+        self.dattn = e(M, h)
+        self.dqkv = e(M, 3 * h)
+        self.dgu = e(M, 2 * f)
+        self.dhmid, self.dhmid2 = e(M, f), e(M, f)
+        self.du = e(M, 3 * r)
+        self.parts = e(M, max(3 * h, f))
+        ldv = (self.V + 7) // 8 * 8
+        self.logits = torch.zeros(min(self.ce_chunk, M), ldv, dtype=BF, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_out = torch.zeros((), dtype=torch.float32, device=dev)
+        self._shape = (B, T)
+
+    # ------------------------------------------------------------------ forward + backward of one micro-batch
+    def _attention(self, qkv: torch.Tensor, train: bool):
+        B, T, nh, hd = self.B_, self.T_, self.nh, self.hd
+        v5 = qkv.view(B, T, 3, nh, hd)
+        q, k, v = (v5[:, :, i].transpose(1, 2) for i in range(3))
+        if train:
+            q, k, v = (t.detach().requires_grad_() for t in (q, k, v))
+            with torch.enable_grad():
+                o = F_.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=True)
+            self._attn_saved.append((o, q, k, v))
+        else:
+            o = F_.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=True)
+        return o.detach().transpose(1, 2).reshape(self.M_, self.h)
+
+    def _lora_group_fwd(self, xn, xd, A, B, W, u, out, *, G, K, Ng, residual=None):
+        """u = s·xd_g·A_gᵀ (grouped) ; out = [xn | u]·[W | B]ᵀ (+ residual)."""
+        g, r, M = fused.gemm, self.r, self.M_
+        drop = self.p > 0 and xd.shape[1] == G * K
+        g(xd, A, u, M=M, N=G * r, K1=K, n_per_group=r, a1_group_kofs=K if drop else 0, alpha=self.scale)
+        g(xn, W, out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=residual)
+
+    def _forward(self, train: bool):
+        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.f, self.r
+        p = self.p if train else 0.0
+        seed = self.seed
+        C.embedding_fwd(self.ids.view(-1), self.W_emb, self.x_in[0])
+        self._attn_saved.clear()
+        for l, S in enumerate(self.layers):
+            sl = l if train else 0
+            x = self.x_in[l] if train else self.x_in[l % 2]
+            x_next = self.x_in[l + 1] if train else self.x_in[(l + 1) % 2]
+            x1 = self.x1[sl]
+            qkv, gu = self.qkv[sl], self.gu[sl]
+            # ---- attention block
+            if p > 0:
+                xd = self.xd_qkv[sl]
+                C.rmsnorm_fwd(x, S.w1, self.xn, self.rstd1[sl], self.eps, xd, seed, S.keys_qkv, p)
+                xn = self.xn
+            else:
+                xn = self.xd_qkv[sl][:, :h] if self.p == 0 else self.xn  # p==0: the normed input is what dA needs
+                xn = xn if xn.is_contiguous() else self.xn
+                C.rmsnorm_fwd(x, S.w1, xn, self.rstd1[sl], self.eps, None, None, [], 0.0)
+                xd = xn
+            self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h)
+            C.rope_inplace(qkv, self.T_, 2 * self.nh, self.hd, self.hd, self.cos, self.sin, False, 0)
+            attn = self._attention(qkv, train)
+            if p > 0:
+                xd_o = self.xd_o[sl]
+                C.dropout_expand(attn, xd_o, seed, [S.key_o], p)
+            else:
+                xd_o = attn
+                if train:
+                    self.xd_o[sl].copy_(attn)
+            self._lora_group_fwd(attn, xd_o, S.A_o, S.B_o, S.Wo, self.u_o[sl], x1, G=1, K=h, Ng=h, residual=x)
+            # ---- MLP block
+            if p > 0:
+                xd = self.xd_gu[sl]
+                C.rmsnorm_fwd(x1, S.w2, self.xn, self.rstd2[sl], self.eps, xd, seed, S.keys_gu, p)
+                xn = self.xn
+            else:
+                xn = self.xd_gu[sl] if self.p == 0 else self.xn
+                C.rmsnorm_fwd(x1, S.w2, xn, self.rstd2[sl], self.eps, None, None, [], 0.0)
+                xd = xn
+            self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f)
+            C.swiglu_fwd(gu, self.hmid)
+            if p > 0:
+                xd_d = self.xd_d[sl]
+                C.dropout_expand(self.hmid, xd_d, seed, [S.key_d], p)
+            else:
+                xd_d = self.hmid
+                if train:
+                    self.xd_d[sl].copy_(self.hmid)
+            self._lora_group_fwd(self.hmid, xd_d, S.A_d, S.B_d, S.Wd, self.u_d[sl], x_next, G=1, K=f, Ng=h, residual=x1)
+        x_last = self.x_in[self.L] if train else self.x_in[self.L % 2]
+        C.rmsnorm_fwd(x_last, self.w_norm, self.xf, self.rstd_f, self.eps, None, None, [], 0.0)
+        return x_last
+
+    def _loss_and_head_backward(self, train: bool):
+        """Chunked LM head + CE.  In training also dxf and dW_head (so logits never persist)."""
+        C, g, M, h, V = self.C, fused.gemm, self.M_, self.h, self.V
+        n_valid = self.B_ * (self.T_ - 1)
+        self.loss_sum.zero_()
+        self.count.zero_()
+        grad_scale = 1.0 / (n_valid * self.ga)
+        for s in range(0, M, self.ce_chunk):
+            m = min(self.ce_chunk, M - s)
+            hc = self.xf[s:s + m]
+            lg = self.logits[:m]
+            g(hc, self.W_head, lg, M=m, N=V, K1=h)
+            C.cross_entropy_fwd_bwd(lg, self.labels[s:s + m], V, grad_scale, -100, self.loss_sum, self.count)
+            if train:
+                g(lg, self.W_head, self.dxf[s:s + m], M=m, N=h, K1=V, b1_mn=True)
+                g(lg, hc, self.gW_head, M=V, N=h, K1=m, a1_mn=True, b1_mn=True, accumulate=True)
+        torch.div(self.loss_sum[0], float(n_valid), out=self.loss_out)
+
+    def _lora_group_bwd(self, dy, S_B, S_W, S_A, gA, gB, xd, u, keys, *, G, K, Ng, base_out, out):
+        """Backward of one stacked LoRA group.  dy [M, G·Ng] -> out [M, K] (grad of the group's input)."""
+        C, g, M, r, s = self.C, fused.gemm, self.M_, self.r, self.scale
+        du = self.du[:, :G * r] if G * r == self.du.shape[1] else self.du.view(-1)[: M * G * r].view(M, G * r)
+        # du_g = s · dy_g · B_g          (B stacked [G·Ng, r], read MN-major; K window g·Ng)
+        g(dy, S_B, du, M=M, N=G * r, K1=Ng, b1_mn=True, n_per_group=r, a1_group_kofs=Ng if G > 1 else 0,
+          b1_group_kofs=Ng if G > 1 else 0, b1_local_n=True, alpha=s)
+        # frozen path: base = dy · W     (W stacked [G·Ng, K], read MN-major)
+        g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
+        # low-rank path per group: part_g = du_g · A_g
+        parts = self.parts.view(-1)[: M * G * K].view(M, G * K)
+        g(du, S_A, parts, M=M, N=G * K, K1=r, b1_mn=True, n_per_group=K, a1_group_kofs=r if G > 1 else 0,
+          b1_group_kofs=r if G > 1 else 0, b1_local_n=True)
+        drop = self.p > 0
+        if drop:
+            C.dropout_combine(base_out, parts, out, self.seed, keys, self.p)
+        else:
+            torch.add(base_out, parts.view(M, G, K).sum(1) if G > 1 else parts, out=out)
+        # weight gradients (fp32, accumulated across micro-batches, split-K over tokens)
+        shared_x = (not drop) or xd.shape[1] != G * K
+        g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+          m_per_group=r if G > 1 else 0, b1_mn_ofs_per_mgroup=0 if shared_x else K)
+        g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+          m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0)
+
+    def _backward(self):
+        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.f, self.r
+        B, T, nh, hd = self.B_, self.T_, self.nh, self.hd
+        dx, dx_other = self.dx_a, self.dx_b
+        C.rmsnorm_bwd(self.dxf, self.x_in[self.L], self.w_norm, self.rstd_f, None, dx, self.gw_norm)
+        for l in range(self.L - 1, -1, -1):
+            S = self.layers[l]
+            # ---- MLP: x_next = hmid·Wdᵀ + u_d·B_dᵀ + x1
+            self._lora_group_bwd(dx, S.B_d, S.Wd, S.A_d, S.gA_d, S.gB_d, self.xd_d[l], self.u_d[l], [S.key_d],
+                                 G=1, K=f, Ng=h, base_out=self.dhmid, out=self.dhmid2)
+            C.swiglu_bwd(self.dhmid2, self.gu[l], self.dgu)
+            self._lora_group_bwd(self.dgu, S.B_gu, S.Wgu, S.A_gu, S.gA_gu, S.gB_gu, self.xd_gu[l], self.u_gu[l], S.keys_gu,
+                                 G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2)
+            C.rmsnorm_bwd(self.dxn2, self.x1[l], S.w2, self.rstd2[l], dx, dx_other, S.gw2)
+            dx, dx_other = dx_other, dx  # dx = grad wrt x1
+            # ---- attention: x1 = attn·Woᵀ + u_o·B_oᵀ + x
+            self._lora_group_bwd(dx, S.B_o, S.Wo, S.A_o, S.gA_o, S.gB_o, self.xd_o[l], self.u_o[l], [S.key_o],
+                                 G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn)
+            o, q, k, v = self._attn_saved[l]
+            dq, dk, dv = torch.autograd.grad(o, (q, k, v), self.dattn.view(B, T, nh, hd).transpose(1, 2))
+            d5 = self.dqkv.view(B, T, 3, nh, hd)
+            d5[:, :, 0].copy_(dq.transpose(1, 2)); d5[:, :, 1].copy_(dk.transpose(1, 2)); d5[:, :, 2].copy_(dv.transpose(1, 2))
+            C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)
+            self._lora_group_bwd(self.dqkv, S.B_qkv, S.Wqkv, S.A_qkv, S.gA_qkv, S.gB_qkv, self.xd_qkv[l], self.u_qkv[l],
+                                 S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2)
+            C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1)
+            dx, dx_other = dx_other, dx
+        C.embedding_bwd(self.ids.view(-1), dx, self.gW_emb, self.pad_idx)
+        self._attn_saved.clear()
+
+    def _micro_body(self):
+        self.labels.view(self.B_, self.T_)[:, :-1].copy_(self.ids[:, 1:])
+        self.labels.view(self.B_, self.T_)[:, -1].fill_(-100)
+        self._forward(True)
+        self._loss_and_head_backward(True)
+        self._backward()
+        self.C.seed_advance(self.seed)
+
+    # ------------------------------------------------------------------ public stepper interface
+    @torch.no_grad()
+    def micro_step(self, input_ids: torch.Tensor) -> torch.Tensor:
+        B, T = input_ids.shape
+        if self._shape != (B, T):
+            self._alloc(B, T)
+            self._graph = None
+        self.ids.copy_(input_ids, non_blocking=True)
+        if not self.use_graphs:
+            self._micro_body()
+            return self.loss_out.clone()
+        if self._graph is None:
+            self._capture()
+        else:
+            self._graph.replay()
+            self._replays += 1
+        return self.loss_out.clone()
+
+    def _capture(self):
+        # warm-up (allocator, cuBLAS/flash workspaces, tensor-map cache) on a side stream, then capture
+        grads_backup = self.store.grads.clone()
+        seed_backup = self.seed.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._micro_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.store.grads.copy_(grads_backup)
+        self.seed.copy_(seed_backup)
+        n0 = self.C.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._micro_body()
+        self._launches_per_micro = self.C.launch_count() - n0
+        # capture does not execute: run the captured work once for this micro-batch
+        self.store.grads.copy_(grads_backup)
+        self.seed.copy_(seed_backup)
+        del grads_backup
+        graph.replay()
+        self._replays += 1
+        self._graph = graph
+
+    @torch.no_grad()
+    def eval_loss(self, input_ids: torch.Tensor) -> torch.Tensor:
+        B, T = input_ids.shape
+        if self._shape != (B, T):
+            self._alloc(B, T)
+            self._graph = None
+        self.ids.copy_(input_ids)
+        self.labels.view(B, T)[:, :-1].copy_(self.ids[:, 1:])
+        self.labels.view(B, T)[:, -1].fill_(-100)
+        self._forward(False)
+        self._loss_and_head_backward(False)
+        return self.loss_out.clone()
+
+    @torch.no_grad()
+    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
+        self.sync.reduce()
+        total, scale = self.sync.grad_norm_and_scale(self.clip)
+        if error_if_nonfinite and not bool(torch.isfinite(total)):
+            raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
+        self.optimizer.step(grad_scale=scale, skip=skip)
+        self.sync.gather_params()
+        self.optimizer.zero_grad()
+        return UpdateInfo(total, False)
+
+    @torch.no_grad()
+    def merge_and_reinit(self):
+        """W += s·B@A on the stacked buffers (tcgen05 GEMM accumulating into W in fp32), then hash re-init."""
+        from ..ops import reference as ref
+
+        g, r = fused.gemm, self.r
+        for S in self.layers:
+            for m in S.mods:
+                g(m.lora_B.weight.data, m.lora_A.weight.data, m.weight.data, M=m.out_features, N=m.in_features, K1=r,
+                  b1_mn=True, alpha=self.scale, accumulate=True)
+                sd = ref.mix_seed(self.model.seed, self.model.n_restarts, m.module_index)
+                self.C.fill_uniform_hash(m.lora_A.weight.data, sd, 1.0 / math.sqrt(m.in_features))
+                m.lora_B.weight.data.zero_()
+        self.model.n_restarts += 1
+
+    def launches_in_window(self, n_steps: int) -> int:
+        """Kernel launches of this extension since ``reset_launch_count`` (graph replays included)."""
+        return int(self.C.launch_count() + self._replays_since_reset() * self._launches_per_micro)
+
+    def _replays_since_reset(self) -> int:
+        return self._replays - getattr(self, "_replay_mark", 0)
+
+    def mark_launch_window(self):
+        self._replay_mark = self._replays
+        self.C.reset_launch_count()
+
+    def set_lr(self, lr: float) -> None:
+        for grp in self.optimizer.param_groups:
+            grp["lr"] = lr

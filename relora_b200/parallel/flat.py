@@ -44,6 +44,7 @@ class FlatParamStore:
         world_size: int = 1,
         grad_dtype: Optional[torch.dtype] = None,
         allocator: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
+        bind_grads: bool = True,
     ):
         if not named_params:
             raise ValueError("no trainable parameters")
@@ -65,12 +66,16 @@ class FlatParamStore:
         self.params = alloc(self.numel, self.dtype, self.device)
         self.grad_dtype = grad_dtype or self.dtype
         self.grads = alloc(self.numel, self.grad_dtype, self.device)
+        # autograd can only accumulate into .grad of the parameter's own dtype; executors that write
+        # gradients themselves (fp32 accumulation for bf16 parameters) keep the views to themselves
+        self.bind_grads = bind_grads and self.grad_dtype == self.dtype
         with torch.no_grad():
             for p, o in zip(self.param_list, self.offsets):
                 view = self.params[o : o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = self.grads[o : o + p.numel()].view(p.shape)
+                if self.bind_grads:
+                    p.grad = self.grads[o : o + p.numel()].view(p.shape)
         self.index: Dict[int, int] = {id(p): i for i, p in enumerate(self.param_list)}
 
     # ------------------------------------------------------------------ views
@@ -84,6 +89,8 @@ class FlatParamStore:
 
     def rebind_grads(self) -> None:
         """Point every ``.grad`` back at its flat view (after ``zero_grad(set_to_none=True)`` etc.)."""
+        if not self.bind_grads:
+            return
         for p, o in zip(self.param_list, self.offsets):
             p.grad = self.grads[o : o + p.numel()].view(p.shape)
 
