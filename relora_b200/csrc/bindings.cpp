@@ -100,7 +100,8 @@ void rmsnorm_fwd(const Tensor& x, const Tensor& w, Tensor& y, Tensor& rstd, doub
                   (float)(1.0 / (1.0 - p)), cur_stream());
 }
 
-void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tensor& rstd, const OptTensor& dx_add, Tensor& dx, Tensor& dw) {
+void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tensor& rstd, const OptTensor& dx_add, Tensor& dx, Tensor& dw,
+                 const OptTensor& ws, const OptTensor& ticket) {
   chk_bf16(dy, "dy"); chk_bf16(x, "x"); chk_bf16(w, "w"); chk_bf16(dx, "dx");
   TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be fp32");
   TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous(), "rmsnorm_bwd: contiguous tensors required");
@@ -109,8 +110,16 @@ void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tenso
   c10::cuda::CUDAGuard guard(x.device());
   const void* add = nullptr;
   if (dx_add.has_value()) { chk_bf16(*dx_add, "dx_add"); TORCH_CHECK(dx_add->is_contiguous()); add = dx_add->data_ptr(); }
+  float* wsp = nullptr;
+  unsigned int* tk = nullptr;
+  if (ws.has_value() && ticket.has_value()) {
+    TORCH_CHECK(ws->scalar_type() == at::kFloat && ws->numel() >= (int64_t)rb::rmsnorm_bwd_ws_blocks() * H, "rmsnorm workspace too small");
+    TORCH_CHECK(ticket->scalar_type() == at::kInt && ticket->numel() >= 1, "ticket must be int32");
+    wsp = ws->data_ptr<float>();
+    tk = reinterpret_cast<unsigned int*>(ticket->data_ptr<int32_t>());
+  }
   rb::rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), add, dx.data_ptr(), dw.data_ptr<float>(), M, H,
-                  cur_stream());
+                  wsp, tk, cur_stream());
 }
 
 void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vector<int64_t> keys, double p) {
@@ -159,6 +168,19 @@ void rope_inplace(Tensor& buf, int64_t T, int64_t n_rot_heads, int64_t hd, int64
   c10::cuda::CUDAGuard guard(buf.device());
   rb::rope_inplace(buf.data_ptr(), buf.stride(0), (int)buf.size(0), (int)T, (int)n_rot_heads, (int)hd, (int)rotary_dim, cos.data_ptr(),
                    sin.data_ptr(), backward, (int)pos0, cur_stream());
+}
+
+void rope_pack_bwd(const Tensor& dq, const Tensor& dk, const Tensor& dv, Tensor& out, int64_t rotary_dim, const Tensor& cos,
+                   const Tensor& sin, int64_t pos0) {
+  chk_bf16(dq, "dq"); chk_bf16(dk, "dk"); chk_bf16(dv, "dv"); chk_bf16(out, "out"); chk_2d_rowmajor(out, "out");
+  TORCH_CHECK(dq.dim() == 4 && dq.stride(3) == 1 && dq.sizes() == dk.sizes() && dq.sizes() == dv.sizes(), "dq/dk/dv must be [B, nh, T, hd]");
+  TORCH_CHECK(dq.strides() == dk.strides() && dq.strides() == dv.strides(), "dq/dk/dv must share strides");
+  const int B = (int)dq.size(0), nh = (int)dq.size(1), T = (int)dq.size(2), hd = (int)dq.size(3);
+  TORCH_CHECK(out.size(0) == (int64_t)B * T && out.size(1) == 3 * (int64_t)nh * hd, "out must be [B*T, 3*nh*hd]");
+  for (const Tensor* t : {&dq, &dk, &dv}) TORCH_CHECK((reinterpret_cast<uintptr_t>(t->data_ptr()) & 15) == 0, "16-byte alignment required");
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::rope_pack_bwd(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dq.stride(0), dq.stride(1), dq.stride(2), out.data_ptr(), out.stride(0), B, T, nh,
+                    hd, (int)rotary_dim, cos.data_ptr(), sin.data_ptr(), (int)pos0, cur_stream());
 }
 
 void swiglu_fwd(const Tensor& gu, Tensor& h) {
@@ -277,9 +299,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_clear_descriptor_cache", &rb::gemm_clear_descriptor_cache);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
   m.def("dropout_expand", &dropout_expand);
   m.def("dropout_combine", &dropout_combine);
   m.def("rope_inplace", &rope_inplace);
+  m.def("rope_pack_bwd", &rope_pack_bwd);
   m.def("swiglu_fwd", &swiglu_fwd);
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("embedding_fwd", &embedding_fwd);

@@ -13,7 +13,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <iostream>
 #include <limits>
 #include <memory>
 #include <random>
@@ -50,12 +49,12 @@ py::array_t<Idx> sample_index(const py::array_t<int32_t>& sizes_, const py::arra
   auto sizes = sizes_.unchecked<1>();
   auto doc_idx = doc_idx_.unchecked<1>();
   const int64_t n_samples = (int64_t(num_epochs) * tokens_per_epoch - 1) / seq_length;
-  std::cout << "    using:\n"
-            << "     number of documents:       " << doc_idx_.shape(0) / num_epochs << "\n"
-            << "     number of epochs:          " << num_epochs << "\n"
-            << "     sequence length:           " << seq_length << "\n"
-            << "     total number of samples:   " << n_samples << "\n"
-            << std::flush;
+  // (python-level print: iostream from an extension loaded next to libtorch's bundled libstdc++ is fragile)
+  py::print("    using:");
+  py::print("     number of documents:      ", doc_idx_.shape(0) / num_epochs);
+  py::print("     number of epochs:         ", num_epochs);
+  py::print("     sequence length:          ", seq_length);
+  py::print("     total number of samples:  ", n_samples);
   std::vector<Idx> out;
   out.reserve(size_t(2 * (n_samples + 1)));
   int64_t cursor = 0;   // position in doc_idx
@@ -104,10 +103,9 @@ void blending_indices(py::array_t<uint8_t>& dataset_index, py::array_t<int64_t>&
     where[t] = taken[size_t(best)]++;
   }
   if (verbose) {
-    std::cout << " > sample ratios:\n";
+    py::print(" > sample ratios:");
     for (int64_t d = 0; d < num_datasets; ++d)
-      std::cout << "   dataset " << d << ", input: " << w[d] << ", achieved: " << double(taken[size_t(d)]) / double(size) << "\n";
-    std::cout << std::flush;
+      py::print("   dataset", d, ", input:", w[d], ", achieved:", double(taken[size_t(d)]) / double(size));
   }
 }
 
@@ -170,7 +168,7 @@ py::array mapping(const py::array_t<int64_t>& docs_, const py::array_t<int32_t>&
       }
     }
   }
-  if (verbose) std::cout << "   will create mapping for " << n_rows << " samples" << std::endl;
+  if (verbose) py::print("   will create mapping for", n_rows, "samples");
   fisher_yates<Idx, 3>(rows, seed);
   return adopt(std::move(rows), {py::ssize_t(n_rows), 3});
 }
@@ -215,7 +213,7 @@ py::array blocks_mapping(const py::array_t<int64_t>& docs_, const py::array_t<in
       }
     }
   }
-  if (verbose) std::cout << "   will create mapping for " << n_rows << " samples" << std::endl;
+  if (verbose) py::print("   will create mapping for", n_rows, "samples");
   fisher_yates<Idx, 4>(rows, seed);
   return adopt(std::move(rows), {py::ssize_t(n_rows), 4});
 }

@@ -65,6 +65,7 @@ void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int 
   if (G > 4) throw std::runtime_error("rmsnorm: at most 4 dropout groups");
   uint4 k = make_uint4(0, 0, 0, 0);
   if (G > 0) k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
+  if (rmsnorm_fwd_warp(x, w, y, rstd, M, H, eps, xd, G, seed_ptr, k, thr24, inv_keep, s)) return;
   const int nvec = H / 8;
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)w;
   bf16 *yp = (bf16*)y, *xdp = (bf16*)xd;
@@ -141,8 +142,9 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
 }
 
 void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw, int M,
-                 int H, cudaStream_t s) {
+                 int H, float* ws, unsigned int* ticket, cudaStream_t s) {
   if (H % 8 != 0 || H > 8192) throw std::runtime_error("rmsnorm_bwd: H must be a multiple of 8 and <= 8192");
+  if (rmsnorm_bwd_warp(dy, x, w, rstd, dx_add, dx, dw, M, H, ws, ticket, s)) return;
   const int nvec = H / 8;
   const int blocks = min(M, num_sms() * 4);
   const int rpb = ceil_div(M, blocks);
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(256) rope_kernel(bf16* __restrict__ buf, long 
 
 void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd, int rotary_dim, const void* cos, const void* sin,
                   bool backward, int pos0, cudaStream_t s) {
+  if (rope_inplace_vec(buf, ld, M, T, n_rot_heads, hd, rotary_dim, cos, sin, backward, pos0, s)) return;
   const int half = rotary_dim / 2;
   if (rotary_dim % 4 != 0 || hd % 2 != 0 || ld % 2 != 0) throw std::runtime_error("rope: rotary_dim must be a multiple of 4");
   const long long total = (long long)M * n_rot_heads * (half / 2);

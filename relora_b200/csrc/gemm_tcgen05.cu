@@ -292,9 +292,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           if (p.split_k > 1) {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-              const uint32_t raw = (i < 32) ? r0[i] : r1[i - 32];
-              if (col0 + i < p.N) atomicAdd(op + i, __uint_as_float(raw) * p.alpha);
+            for (int q = 0; q < 16; ++q) {
+              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
+              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
+              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
+              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              if (out_vec && col0 + q * 4 + 4 <= p.N) {  // one 16-byte vector reduction instead of four scalar atomics
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + q * 4), "f"(a0), "f"(a1), "f"(a2), "f"(a3)
+                             : "memory");
+              } else {
+                const float e[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col0 + q * 4 + i < p.N) atomicAdd(op + q * 4 + i, e[i]);
+              }
             }
           } else if (p.out_f32) {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;

@@ -11,8 +11,15 @@ namespace rb {
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
                  const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s);
 // dx = rstd * (g - xhat * mean(g * xhat)) with g = dy * w (+ dx_add);  dw_f32[H] += sum_m dy * bf16(xhat)
+// `ws` (fp32 [rmsnorm_bwd_ws_blocks(), H]) + `ticket` (zeroed uint32) enable the warp-per-row kernel (H <= 2048); without
+// them the block-per-row fallback with global atomics on dw is used.
 void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw,
-                 int M, int H, cudaStream_t s);
+                 int M, int H, float* ws, unsigned int* ticket, cudaStream_t s);
+int rmsnorm_bwd_ws_blocks();
+bool rmsnorm_fwd_warp(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
+                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr24, float inv_keep, cudaStream_t s);
+bool rmsnorm_bwd_warp(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw, int M,
+                      int H, float* ws, unsigned int* ticket, cudaStream_t s);
 
 // xd[m, g*H + k] = keep(seed_g, m, k) ? x[m,k] / (1-p) : 0
 void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys,
@@ -27,6 +34,13 @@ void dropout_combine(const void* base, const void* parts, long long part_stride,
 // rotary_dim <= hd leading dims of each head; position of row m is (m % T) + pos0.  cos/sin: bf16 [*, rotary_dim].
 void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd, int rotary_dim, const void* cos,
                   const void* sin, bool backward, int pos0, cudaStream_t s);
+
+bool rope_inplace_vec(void* buf, long long ld, int M, int T, int n_rot_heads, int hd, int rotary_dim, const void* cos,
+                      const void* sin, bool backward, int pos0, cudaStream_t s);
+// dqkv[b*T+t, which*nh*hd + h*hd + d] <- inverse-rotated dq / dk and dv, each [B, nh, T, hd] with strides (sB, sH, sT, 1)
+void rope_pack_bwd(const void* dq, const void* dk, const void* dv, long long sB, long long sH, long long sT, void* out,
+                   long long ldo, int B, int T, int nh, int hd, int rotary_dim, const void* cos, const void* sin, int pos0,
+                   cudaStream_t s);
 
 // ---- SwiGLU --------------------------------------------------------------------------------
 // gu: [M, 2F] (gate | up) -> h[M, F] = silu(gate) * up

@@ -371,7 +371,8 @@ class FusedLlamaStepper:
         C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.f, self.r
         B, T, nh, hd = self.B_, self.T_, self.nh, self.hd
         dx, dx_other = self.dx_a, self.dx_b
-        C.rmsnorm_bwd(self.dxf, self.x_in[self.L], self.w_norm, self.rstd_f, None, dx, self.gw_norm)
+        ws, tk = fused.norm_workspace(self.device, h)
+        C.rmsnorm_bwd(self.dxf, self.x_in[self.L], self.w_norm, self.rstd_f, None, dx, self.gw_norm, ws, tk)
         for l in range(self.L - 1, -1, -1):
             S = self.layers[l]
             # ---- MLP: x_next = hmid·Wdᵀ + u_d·B_dᵀ + x1
@@ -380,19 +381,22 @@ class FusedLlamaStepper:
             C.swiglu_bwd(self.dhmid2, self.gu[l], self.dgu)
             self._lora_group_bwd(self.dgu, S.B_gu, S.Wgu, S.A_gu, S.gA_gu, S.gB_gu, self.xd_gu[l], self.u_gu[l], S.keys_gu,
                                  G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2)
-            C.rmsnorm_bwd(self.dxn2, self.x1[l], S.w2, self.rstd2[l], dx, dx_other, S.gw2)
+            C.rmsnorm_bwd(self.dxn2, self.x1[l], S.w2, self.rstd2[l], dx, dx_other, S.gw2, ws, tk)
             dx, dx_other = dx_other, dx  # dx = grad wrt x1
             # ---- attention: x1 = attn·Woᵀ + u_o·B_oᵀ + x
             self._lora_group_bwd(dx, S.B_o, S.Wo, S.A_o, S.gA_o, S.gB_o, self.xd_o[l], self.u_o[l], [S.key_o],
                                  G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn)
             o, q, k, v = self._attn_saved[l]
             dq, dk, dv = torch.autograd.grad(o, (q, k, v), self.dattn.view(B, T, nh, hd).transpose(1, 2))
-            d5 = self.dqkv.view(B, T, 3, nh, hd)
-            d5[:, :, 0].copy_(dq.transpose(1, 2)); d5[:, :, 1].copy_(dk.transpose(1, 2)); d5[:, :, 2].copy_(dv.transpose(1, 2))
-            C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)
+            if dq.stride() == dk.stride() == dv.stride() and dq.stride(3) == 1:
+                C.rope_pack_bwd(dq, dk, dv, self.dqkv, hd, self.cos, self.sin, 0)  # gather + inverse rotation in one pass
+            else:
+                d5 = self.dqkv.view(B, T, 3, nh, hd)
+                d5[:, :, 0].copy_(dq.transpose(1, 2)); d5[:, :, 1].copy_(dk.transpose(1, 2)); d5[:, :, 2].copy_(dv.transpose(1, 2))
+                C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)
             self._lora_group_bwd(self.dqkv, S.B_qkv, S.Wqkv, S.A_qkv, S.gA_qkv, S.gB_qkv, self.xd_qkv[l], self.u_qkv[l],
                                  S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2)
-            C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1)
+            C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1, ws, tk)
             dx, dx_other = dx_other, dx
         C.embedding_bwd(self.ids.view(-1), dx, self.gW_emb, self.pad_idx)
         self._attn_saved.clear()

@@ -109,6 +109,20 @@ def gemm(
 
 
 # ----------------------------------------------------------------------------- RMSNorm
+_norm_ws = {}
+
+
+def norm_workspace(device, H: int):
+    """(fp32 workspace, int32 ticket) for the warp-per-row RMSNorm backward (shared by all layers of a device)."""
+    key = (device.type, device.index)
+    cur = _norm_ws.get(key)
+    need = _C().rmsnorm_bwd_ws_blocks() * H
+    if cur is None or cur[0].numel() < need:
+        cur = (torch.empty(need, dtype=torch.float32, device=device), torch.zeros(1, dtype=torch.int32, device=device))
+        _norm_ws[key] = cur
+    return cur
+
+
 class _RMSNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, eps):
@@ -124,7 +138,8 @@ class _RMSNormFn(torch.autograd.Function):
         x, weight, rstd = ctx.saved_tensors
         dx = torch.empty_like(x)
         dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
-        _C().rmsnorm_bwd(dy.contiguous(), x, weight.contiguous(), rstd, None, dx, dw)
+        ws, tk = norm_workspace(x.device, x.shape[-1])
+        _C().rmsnorm_bwd(dy.contiguous(), x, weight.contiguous(), rstd, None, dx, dw, ws, tk)
         return dx, dw.to(weight.dtype), None
 
 

@@ -140,7 +140,13 @@ def test_rmsnorm_fwd_bwd(C, M, H):
     ref.rmsnorm_fp32(xf, wf, 1e-6).backward(dy.float())
     dx = torch.empty_like(x)
     dw = torch.zeros(H, device="cuda", dtype=torch.float32)
-    C.rmsnorm_bwd(dy, x, w, rstd, None, dx, dw)
+    from relora_b200.ops import fused
+
+    ws, tk = fused.norm_workspace(x.device, H)
+    C.rmsnorm_bwd(dy, x, w, rstd, None, dx, dw, ws, tk)
+    dx2, dw2 = torch.empty_like(x), torch.zeros(H, device="cuda", dtype=torch.float32)
+    C.rmsnorm_bwd(dy, x, w, rstd, None, dx2, dw2, None, None)  # block-per-row fallback
+    assert _relerr(dx2, dx) < 1e-5 and _relerr(dw2, dw) < 1e-4
     assert _relerr(dx, xf.grad) < 1e-2
     assert _relerr(dw, wf.grad) < 1e-2
 
@@ -188,6 +194,28 @@ def test_rope_fwd_bwd(C, hd, rot):
     # backward is the inverse rotation
     C.rope_inplace(buf, T, 2 * nh, hd, rot, cos, sin, True, 0)
     assert _relerr(buf, orig) < 1.5e-2
+
+
+@pytest.mark.parametrize("hd,rot", [(48, 48), (64, 64), (64, 16)])
+def test_rope_pack_bwd(C, hd, rot):
+    from relora_b200.ops import reference as ref
+
+    torch.manual_seed(1)
+    B, T, nh = 2, 24, 4
+    cos, sin = ref.rope_tables(rot, 32, device="cuda", dtype=BF)
+    # gradients as attention backward returns them: [B, nh, T, hd] views of [B, T, nh, hd] memory
+    dq, dk, dv = (_rand(B, T, nh, hd).transpose(1, 2) for _ in range(3))
+    out = torch.empty(B * T, 3 * nh * hd, device="cuda", dtype=BF)
+    C.rope_pack_bwd(dq, dk, dv, out, rot, cos, sin, 0)
+    want = torch.empty_like(out)
+    w5 = want.view(B, T, 3, nh, hd)
+    w5[:, :, 0].copy_(dq.transpose(1, 2)); w5[:, :, 1].copy_(dk.transpose(1, 2)); w5[:, :, 2].copy_(dv.transpose(1, 2))
+    C.rope_inplace(want, T, 2 * nh, hd, rot, cos, sin, True, 0)
+    assert _relerr(out, want) < 1e-6
+    # contiguous [B, nh, T, hd] inputs work too
+    out2 = torch.empty_like(out)
+    C.rope_pack_bwd(dq.contiguous(), dk.contiguous(), dv.contiguous(), out2, rot, cos, sin, 0)
+    assert torch.equal(out, out2)
 
 
 def test_swiglu(C):
