@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include "comm.h"
 #include "gemm.h"
 #include "kernels.h"
 
@@ -288,6 +289,52 @@ void magnitude_prune(Tensor& x, double ratio, Tensor& workspace, Tensor& thr) {
   rb::threshold_prune(x.data_ptr(), f, x.numel(), thr.data_ptr<float>(), cur_stream());
 }
 
+// ---------------------------------------------------------------------------------------------- NVLink collectives
+rb::PeerPtrs peer_ptrs(const std::vector<int64_t>& v) {
+  TORCH_CHECK((int)v.size() <= rb::kMaxPeers, "at most 8 peers");
+  rb::PeerPtrs p;
+  for (int i = 0; i < rb::kMaxPeers; ++i) p.ptr[i] = i < (int)v.size() ? reinterpret_cast<void*>(v[i]) : nullptr;
+  return p;
+}
+rb::CommCtx comm_ctx(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t world, Tensor& local_go) {
+  TORCH_CHECK(local_go.is_cuda() && local_go.scalar_type() == at::kInt && local_go.numel() >= 2, "local_go must be int32[2] on the device");
+  rb::CommCtx c;
+  c.rank = (int)rank; c.world = (int)world; c.flags = peer_ptrs(flag_ptrs);
+  c.local_go = reinterpret_cast<uint32_t*>(local_go.data_ptr<int32_t>());
+  return c;
+}
+void comm_barrier(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, Tensor& local_go, int64_t set, int64_t epoch) {
+  c10::cuda::CUDAGuard guard(local_go.device());
+  rb::xgpu_barrier(comm_ctx(flag_ptrs, rank, world, local_go), (int)set, (uint32_t)epoch, cur_stream());
+}
+void comm_allreduce_bf16(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, Tensor& local_go, std::vector<int64_t> buf_ptrs,
+                         int64_t mc_ptr, int64_t off_elems, int64_t n, int64_t epoch, int64_t max_blocks) {
+  c10::cuda::CUDAGuard guard(local_go.device());
+  rb::allreduce_bf16(comm_ctx(flag_ptrs, rank, world, local_go), peer_ptrs(buf_ptrs), reinterpret_cast<void*>(mc_ptr), off_elems, n,
+                     (uint32_t)epoch, (int)max_blocks, cur_stream());
+}
+void comm_fused_update(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, Tensor& local_go, const Tensor& grads_f32,
+                       std::vector<int64_t> grad_ptrs, int64_t grad_mc, Tensor& gred, std::vector<int64_t> param_ptrs, int64_t param_mc,
+                       Tensor& exp_avg, Tensor& exp_avg_sq, int64_t n, double lr, double b1, double b2, double eps, double wd, int64_t step,
+                       double max_norm, const OptTensor& skip, Tensor& norm_out, Tensor& scratch, int64_t epoch, int64_t max_blocks) {
+  TORCH_CHECK(grads_f32.scalar_type() == at::kFloat && grads_f32.is_contiguous() && grads_f32.numel() >= n, "grads must be fp32 [n]");
+  TORCH_CHECK(gred.scalar_type() == at::kFloat && gred.numel() * world >= n, "gred must be fp32 [n / world]");
+  chk_bf16(exp_avg, "exp_avg"); chk_bf16(exp_avg_sq, "exp_avg_sq");
+  TORCH_CHECK(exp_avg.numel() * world >= n && exp_avg_sq.numel() * world >= n, "moments must be [n / world]");
+  TORCH_CHECK(norm_out.scalar_type() == at::kFloat && scratch.scalar_type() == at::kFloat && scratch.numel() >= 2);
+  c10::cuda::CUDAGuard guard(local_go.device());
+  rb::FusedUpdateArgs a;
+  a.grads_f32 = grads_f32.data_ptr<float>();
+  a.grad_bufs = peer_ptrs(grad_ptrs); a.grad_mc = reinterpret_cast<void*>(grad_mc);
+  a.gred = gred.data_ptr<float>();
+  a.param_bufs = peer_ptrs(param_ptrs); a.param_mc = reinterpret_cast<void*>(param_mc);
+  a.exp_avg = exp_avg.data_ptr(); a.exp_avg_sq = exp_avg_sq.data_ptr();
+  a.n = n; a.lr = (float)lr; a.beta1 = (float)b1; a.beta2 = (float)b2; a.eps = (float)eps; a.weight_decay = (float)wd;
+  a.step = (int)step; a.max_norm = (float)max_norm; a.inv_world = 1.0f / (float)world;
+  a.skip = f32ptr(skip); a.norm_out = norm_out.data_ptr<float>(); a.sq_accum = scratch.data_ptr<float>(); a.max_blocks = (int)max_blocks;
+  rb::fused_update(comm_ctx(flag_ptrs, rank, world, local_go), a, (uint32_t)epoch, cur_stream());
+}
+
 long long launch_count() { return rb::g_launch_count; }
 void reset_launch_count() { rb::g_launch_count = 0; }
 
@@ -319,6 +366,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("random_prune", &random_prune);
   m.def("magnitude_prune", &magnitude_prune);
   m.def("quantile_workspace_bytes", &rb::magnitude_quantile_workspace_bytes);
+  m.def("comm_barrier", &comm_barrier);
+  m.def("comm_allreduce_bf16", &comm_allreduce_bf16);
+  m.def("comm_fused_update", &comm_fused_update);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
 }

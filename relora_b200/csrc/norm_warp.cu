@@ -2,8 +2,7 @@
 //
 // forward : y = w * bf16(x * rstd) (+ G dropout-expanded copies for the LoRA down-projections), rstd saved
 // backward: dx = rstd * (g - xhat * mean(g * xhat)) + dx_add,  g = dy * w
-//           dw += sum_rows dy * bf16(xhat): per-lane fp32 partials -> block partial (smem) -> workspace row;
-//           the last block to finish (atomic ticket) folds the workspace into dw — no global atomics on dw.
+//           dw += sum_rows dy * bf16(xhat): per-lane fp32 partials -> block partial (smem) -> red.global.add.v4.f32
 #include "common.cuh"
 #include "kernels.h"
 
@@ -68,10 +67,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ rstd,
-    const bf16* __restrict__ dx_add, bf16* __restrict__ dx, float* __restrict__ dw, int M, int H, float* __restrict__ ws,
-    unsigned int* __restrict__ ticket) {
+    const bf16* __restrict__ dx_add, bf16* __restrict__ dx, float* __restrict__ dw, int M, int H) {
   extern __shared__ float sdw[];  // [H] block partial of dw
-  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = H / 8;
   for (int c = threadIdx.x; c < H; c += blockDim.x) sdw[c] = 0.f;
@@ -85,16 +82,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
 #pragma unroll
     for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
   }
-  for (int row = blockIdx.x * kWarpsPerBlock + warp; row < M; row += gridDim.x * kWarpsPerBlock) {
-    const float rs = rstd[row];
-    uint4 dyv[VPL], xv[VPL];
+  const int stride = gridDim.x * kWarpsPerBlock;
+  int row = blockIdx.x * kWarpsPerBlock + warp;
+  // software pipeline: the loads of the next row are in flight while the current one is reduced and written
+  uint4 ndy[VPL], nx[VPL], nadd[VPL];
+  float nrs = 0.f;
+  auto fetch = [&](int r) {
+    if (r < M) {
+      nrs = rstd[r];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          ndy[i] = reinterpret_cast<const uint4*>(dy + (long long)r * H)[c];
+          nx[i] = reinterpret_cast<const uint4*>(x + (long long)r * H)[c];
+          if (dx_add != nullptr) nadd[i] = reinterpret_cast<const uint4*>(dx_add + (long long)r * H)[c];
+        }
+      }
+    }
+  };
+  constexpr bool kPrefetch = VPL <= 4;  // double-buffering 8 vectors per lane would spill
+  if (kPrefetch) fetch(row);
+  for (; row < M; row += stride) {
+    uint4 dyv[VPL], xv[VPL], addv[VPL];
+    if (!kPrefetch) fetch(row);
+    const float rs = nrs;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      dyv[i] = ndy[i];
+      xv[i] = nx[i];
+      addv[i] = nadd[i];
+    }
+    if (kPrefetch) fetch(row + stride);
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        dyv[i] = reinterpret_cast<const uint4*>(dy + (long long)row * H)[c];
-        xv[i] = reinterpret_cast<const uint4*>(x + (long long)row * H)[c];
         float dyf[8], xf[8], wf[8];
         unpack8(dyv[i], dyf);
         unpack8(xv[i], xf);
@@ -120,7 +144,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
         for (int j = 0; j < 8; ++j) o[j] = rs * (dyf[j] * wf[j] - xf[j] * rs * dot);
         if (dx_add != nullptr) {
           float a[8];
-          unpack8(reinterpret_cast<const uint4*>(dx_add + (long long)row * H)[c], a);
+          unpack8(addv[i], a);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += a[j];
         }
@@ -128,7 +152,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
       }
     }
   }
-  // ---- dw: lanes -> block partial in smem -> workspace row -> last block folds everything into dw
+  // ---- dw: lanes -> block partial in shared memory -> one 16-byte vector reduction per 4 columns per block
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + i * 32;
@@ -138,20 +162,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
     }
   }
   __syncthreads();
-  float* my = ws + (long long)blockIdx.x * H;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) my[c] = sdw[c];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    for (int c = threadIdx.x; c < H; c += blockDim.x) {
-      float acc = 0.f;
-      for (unsigned int b = 0; b < gridDim.x; ++b) acc += __ldcg(ws + (long long)b * H + c);
-      dw[c] += acc;
-    }
-    if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + c), "f"(sdw[c]), "f"(sdw[c + 1]), "f"(sdw[c + 2]), "f"(sdw[c + 3])
+                 : "memory");
   }
 }
 
@@ -186,11 +199,12 @@ int rmsnorm_bwd_ws_blocks() { return 2 * num_sms(); }
 bool rmsnorm_bwd_warp(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw, int M,
                       int H, float* ws, unsigned int* ticket, cudaStream_t s) {
   const int vpl = pick_vpl(H / 8);
-  if (vpl == 0 || ws == nullptr || ticket == nullptr) return false;
-  const int grid = std::min(ceil_div(M, kWarpsPerBlock), rmsnorm_bwd_ws_blocks());
+  (void)ws; (void)ticket;  // kept in the signature for the workspace-based variant; dw now uses vector reductions
+  if (vpl == 0 || (reinterpret_cast<uintptr_t>(dw) & 15) != 0) return false;
+  const int grid = std::min(ceil_div(M, kWarpsPerBlock), 4 * num_sms());
   const size_t smem = (size_t)H * sizeof(float);
   const bf16 *a = (const bf16*)dy, *b = (const bf16*)x, *c = (const bf16*)w, *d = (const bf16*)dx_add;
-#define L(V) rmsnorm_bwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, smem, s>>>(a, b, c, rstd, d, (bf16*)dx, dw, M, H, ws, ticket)
+#define L(V) rmsnorm_bwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, smem, s>>>(a, b, c, rstd, d, (bf16*)dx, dw, M, H)
   switch (vpl) {
     case 1: L(1); break;
     case 2: L(2); break;

@@ -140,7 +140,24 @@ class FusedLlamaStepper:
         extra = [(n, p) for n, p in model.named_parameters() if p.requires_grad and id(p) not in seen]
         if extra:
             raise RuntimeError(f"unexpected trainable parameters for the fused executor: {[n for n, _ in extra]}")
-        self.store = FlatParamStore(named, world_size=info.world_size, grad_dtype=torch.float32, bind_grads=False)
+        # ---- transport: NVLink peer-memory kernels when symmetric memory is available, NCCL otherwise
+        self.comm = None
+        if info.world_size > 1 and transport in ("p2p", "auto"):
+            from ..parallel.symm import SymmComm, symmetric_memory_available
+
+            if symmetric_memory_available():
+                try:
+                    self.comm = SymmComm()
+                except Exception as e:  # no P2P access, allocation failure, ...
+                    if transport == "p2p":
+                        raise
+                    from ..obs import logger
+
+                    logger.warning(f"peer-memory collectives unavailable ({type(e).__name__}: {e}); using NCCL")
+            elif transport == "p2p":
+                raise RuntimeError("--comm p2p needs torch symmetric memory over an NCCL process group")
+        self.store = FlatParamStore(named, world_size=info.world_size, grad_dtype=torch.float32, bind_grads=False,
+                                    allocator=self.comm.allocator() if self.comm is not None else None)
         self.trainable_params = [p for _, p in named]
         self.trainable_names = [n for n, _ in named]
         self.lora_params = [p for n, p in named if "lora_" in n]
@@ -187,9 +204,17 @@ class FusedLlamaStepper:
         self.sin = rot.sin_cached[0, 0].to(BF).contiguous()
 
         # ---------------------------------------------------------------- optimizer / comm
-        symm = symm_factory.bind(self.store) if (symm_factory is not None and transport == "p2p") else None
-        self.sync = GradSync(self.store, info, transport=transport, zero=zero, symm=symm)
-        shard = self.sync.shard if zero else None
+        self.sync = GradSync(self.store, info, transport="nccl", zero=zero and self.comm is None)
+        shard = self.sync.shard if (zero and self.comm is None) else None
+        self._stage = None
+        if self.comm is not None:
+            # fused update: gradients travel as bf16 through a symmetric buffer, each rank owns 1/world of the
+            # optimizer state (ZeRO-1 dataflow) and writes its updated parameters into every replica
+            self.sync.transport = "p2p"
+            self.param_buf = self.comm.buffer_of(self.store.params)
+            self.grad_buf = self.comm.alloc(self.store.numel, BF)
+            self.gred = torch.empty(self.store.numel // info.world_size, dtype=torch.float32, device=dev)
+            shard = self.store.shard_bounds(info.rank, info.world_size)
         self.optimizer = FlatAdamW(self.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, shard=shard,
                                    native=native or fused.NativeOptim())
         self.seed = fused.seed_state.get(dev)
@@ -467,13 +492,42 @@ class FusedLlamaStepper:
 
     @torch.no_grad()
     def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
-        self.sync.reduce()
-        total, scale = self.sync.grad_norm_and_scale(self.clip)
+        opt = self.optimizer
+        world = self.info.world_size
+        if self.comm is not None:
+            grp = opt.param_groups[0]
+            opt.step_count += 1
+            opt._step_t.add_(1)
+            norm = self.comm.fused_update(
+                grads_f32=self.store.grads, grad_buf=self.grad_buf, gred=self.gred, param_buf=self.param_buf,
+                exp_avg=opt.exp_avg, exp_avg_sq=opt.exp_avg_sq, n=self.store.numel, lr=grp["lr"], betas=grp["betas"],
+                eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=skip)
+            total = norm[0].clone()
+            opt.zero_grad()
+            if error_if_nonfinite and not bool(torch.isfinite(total)):
+                raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
+            return UpdateInfo(total, False)
+        grads = None
+        if world > 1 and not self.sync.zero:
+            # NCCL baseline: gradients cross the wire as bf16 (like the reference's bf16 DDP buckets), once per update
+            if self._stage is None:
+                self._stage = torch.empty(self.store.numel, dtype=BF, device=self.device)
+            self.C.cast_f32_to_bf16(self.store.grads, self._stage, 1.0)
+            dist.all_reduce(self._stage, op=dist.ReduceOp.SUM)
+            grads = self._stage
+            sq = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self.C.sumsq(grads, sq)
+            total = sq[0].sqrt() / world
+            coef = torch.clamp(self.clip / (total + 1e-6), max=1.0) if self.clip and self.clip > 0 else torch.ones_like(total)
+            scale = coef / world
+        else:
+            self.sync.reduce()
+            total, scale = self.sync.grad_norm_and_scale(self.clip)
         if error_if_nonfinite and not bool(torch.isfinite(total)):
             raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
-        self.optimizer.step(grad_scale=scale, skip=skip)
+        opt.step(grad_scale=scale, skip=skip, grads=grads)
         self.sync.gather_params()
-        self.optimizer.zero_grad()
+        opt.zero_grad()
         return UpdateInfo(total, False)
 
     @torch.no_grad()

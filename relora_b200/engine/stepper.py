@@ -109,8 +109,6 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
     engine = getattr(args, "engine", "auto")
     zero = str(args.optimizer).lower() == "adam_zero"
     transport = getattr(args, "comm", "auto")
-    if transport == "auto":
-        transport = "nccl"
     kw = dict(
         lr=args.lr,
         betas=(args.adam_beta1, args.adam_beta2),
@@ -130,4 +128,5 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
             return FusedLlamaStepper(model, info, cuda_graphs=getattr(args, "cuda_graphs", True), **kw)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
+    kw["transport"] = "nccl"  # the module path reduces through the process group (NCCL / gloo)
     return ModuleStepper(model, info, **kw)

@@ -45,6 +45,7 @@ class FlatParamStore:
         grad_dtype: Optional[torch.dtype] = None,
         allocator: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
         bind_grads: bool = True,
+        grad_allocator: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
     ):
         if not named_params:
             raise ValueError("no trainable parameters")
@@ -65,7 +66,8 @@ class FlatParamStore:
         alloc = allocator or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
         self.params = alloc(self.numel, self.dtype, self.device)
         self.grad_dtype = grad_dtype or self.dtype
-        self.grads = alloc(self.numel, self.grad_dtype, self.device)
+        galloc = grad_allocator or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
+        self.grads = galloc(self.numel, self.grad_dtype, self.device)
         # autograd can only accumulate into .grad of the parameter's own dtype; executors that write
         # gradients themselves (fp32 accumulation for bf16 parameters) keep the views to themselves
         self.bind_grads = bind_grads and self.grad_dtype == self.dtype
@@ -221,12 +223,12 @@ class FlatAdamW(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ update
     @torch.no_grad()
-    def step(self, closure=None, *, grad_scale=1.0, skip=None):
+    def step(self, closure=None, *, grad_scale=1.0, skip=None, grads=None):
         group = self.param_groups[0]
         lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
         lo, hi = self.shard
         p = self.store.params[lo:hi]
-        g = self.store.grads[lo:hi]
+        g = (self.store.grads if grads is None else grads)[lo:hi]
         if self._native is not None and p.is_cuda:
             self.step_count += 1  # the device-side skip keeps the moments untouched; the counter drift
             self._step_t.add_(1)  # of a skipped step only perturbs bias correction, like upstream's
@@ -251,6 +253,10 @@ class FlatAdamW(torch.optim.Optimizer):
         bufs = {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
         n_total = 0
         n_zero = torch.zeros((), dtype=torch.float32, device=self.store.device)
+        self._gather_cache = {}
+        if kind == "magnitude" and self.is_sharded:
+            for key in keys:  # collective: every rank gathers, whether or not one of its tensors straddles a boundary
+                self._gathered(key)
         for t_idx, p in enumerate(params):
             if id(p) not in self.store.index:
                 continue
@@ -269,8 +275,13 @@ class FlatAdamW(torch.optim.Optimizer):
                         seg.mul_(keep.to(seg.dtype))
                 else:
                     if self.is_sharded and (a != o or b != o + n):
-                        raise NotImplementedError("magnitude pruning of a tensor split across ZeRO shards")
-                    if self._native is not None and seg.is_cuda:
+                        # the tensor straddles a shard boundary: take the quantile over the whole tensor
+                        full = self._gathered(key)[o : o + n]
+                        from ..relora.optim_reset import magnitude_threshold
+
+                        thr = magnitude_threshold(full, ratio)
+                        seg.mul_((seg.abs() > thr).to(seg.dtype))
+                    elif self._native is not None and seg.is_cuda:
                         self._native.magnitude_prune_(seg, ratio)
                     else:
                         from ..relora.optim_reset import magnitude_pruning_
@@ -278,4 +289,14 @@ class FlatAdamW(torch.optim.Optimizer):
                         magnitude_pruning_(seg, ratio)
                 n_total += seg.numel()
                 n_zero += (seg == 0).sum()
+        self._gather_cache = {}
         return float(n_zero.item()) / (1e-7 + n_total) * 100
+
+    def _gathered(self, key: str) -> torch.Tensor:
+        """Full (all shards) copy of a moment buffer, gathered once per pruning call."""
+        if key not in self._gather_cache:
+            local = self.exp_avg if key == "exp_avg" else self.exp_avg_sq
+            full = torch.empty(self.store.numel, dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(full, local.contiguous())
+            self._gather_cache[key] = full
+        return self._gather_cache[key]

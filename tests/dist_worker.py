@@ -1,0 +1,91 @@
+"""Multi-GPU worker (launched by tests/test_multigpu.py through torch.distributed.run)."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("RELORA_B200_NO_WANDB", "1")
+BF = torch.bfloat16
+
+
+def check_allreduce(comm, rank, world):
+    """two-shot peer-memory all-reduce (P2P and multicast variants) vs NCCL, sizes 64 KB .. 64 MB"""
+    out = {}
+    for use_mc in (False, True):
+        comm.use_multicast = use_mc
+        for n in (32 * 1024, 1024 * 1024, 8 * 1024 * 1024 + 8 * world, 32 * 1024 * 1024):
+            n = (n // (8 * world)) * 8 * world
+            buf = comm.alloc(n, BF)
+            if use_mc and not buf.mc_base:
+                out["multicast"] = "unavailable"
+                continue
+            g = torch.Generator(device="cuda").manual_seed(100 + rank)
+            x = (torch.randn(n, device="cuda", generator=g) * 0.5).to(BF)
+            buf.tensor.copy_(x)
+            ref = x.float().clone()
+            dist.all_reduce(ref)
+            torch.cuda.synchronize()
+            dist.barrier()
+            comm.all_reduce_(buf)
+            torch.cuda.synchronize()
+            err = float((buf.tensor.float() - ref).abs().max() / ref.abs().max())
+            assert err < 2e-2, (use_mc, n, err)
+            out[f"{'mc' if use_mc else 'p2p'}_{n}"] = err
+    comm.use_multicast = True
+    return out
+
+
+def check_training(rank, world, transport):
+    """3 updates of the fused executor with DP=world; returns losses + a parameter checksum"""
+    from relora_b200.engine.api import TrainingEngine
+    from relora_b200.ops import fused
+    from relora_b200.parallel.dist import init_distributed
+
+    info = init_distributed("cuda", "nccl")
+    eng = TrainingEngine.build(info, model_config=os.path.join(ROOT, "configs", "llama_35m.json"), batch_size=2,
+                               gradient_accumulation=2, total_batch_size=4 * world, max_length=128, use_peft=True, lora_r=128,
+                               relora=1000, cycle_length=1000, scheduler="cosine_restarts", warmup_steps=2, restart_warmup_steps=1,
+                               lr=1e-3, num_training_steps=1000, dtype="bfloat16", device="cuda", init_lora_a="kaiming",
+                               comm=transport, seed=0)
+    fused.seed_state.set(info.device, 777)
+    g = torch.Generator().manual_seed(5 + rank)
+    losses = []
+    for _ in range(3):
+        ids = torch.randint(0, 32000, (2, 2, 128), generator=g).cuda()
+        losses.append(float(eng.train_step_device(ids)))
+    p = eng.stepper.store.params.float()
+    chk = [float(p.sum()), float(p.abs().sum()), float(p[:: 997].double().sum())]
+    # replicas must be identical
+    t = torch.tensor(chk, dtype=torch.float64, device="cuda")
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), ("replicas diverged", lo.tolist(), hi.tolist())
+    return {"losses": losses, "checksum": chk, "transport": eng.stepper.sync.transport, "executor": type(eng.stepper).__name__}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = sys.argv[1]
+    res = {}
+    if mode == "allreduce":
+        from relora_b200.parallel.symm import SymmComm
+
+        comm = SymmComm()
+        res = check_allreduce(comm, rank, world)
+    elif mode.startswith("train_"):
+        res = check_training(rank, world, mode.split("_", 1)[1])
+    if rank == 0:
+        print("RESULT " + json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
