@@ -120,10 +120,21 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const CommCtx c, const P
   const long long per = (n_vec + c.world - 1) / c.world;
   const long long lo = off_vec + per * c.rank;
   const long long hi = min(off_vec + n_vec, lo + per);
-  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    float acc[8];
-    reduce_vec(bufs, mc, c.world, c.rank, i, acc);
-    broadcast_vec(bufs, mc, c.world, i, pack8(acc));
+  // four independent vectors per thread per trip keep enough loads in flight to cover the ~2 us NVLink round trip
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+    float acc[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) reduce_vec(bufs, mc, c.world, c.rank, i, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) broadcast_vec(bufs, mc, c.world, i, pack8(acc[u]));
+    }
   }
   __threadfence_system();
   __syncthreads();

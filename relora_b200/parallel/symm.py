@@ -31,8 +31,9 @@ def symmetric_memory_available() -> bool:
     if not (dist.is_initialized() and torch.cuda.is_available() and dist.get_backend() == "nccl"):
         return False
     try:
-        import torch.distributed._symmetric_memory  # noqa: F401
+        import importlib
 
+        importlib.import_module("torch.distributed._symmetric_memory")
         return True
     except Exception:
         return False
@@ -61,7 +62,7 @@ class SymmBuffer:
 
 
 class SymmComm:
-    def __init__(self, group=None, use_multicast: Optional[bool] = None, max_blocks: int = 64):
+    def __init__(self, group=None, use_multicast: Optional[bool] = None, max_blocks: int = 128):
         import torch.distributed._symmetric_memory as symm_mem
 
         self._symm = symm_mem
