@@ -138,7 +138,9 @@ def collate_input_ids(samples) -> Dict[str, torch.Tensor]:
     if isinstance(first, torch.Tensor):
         ids = torch.stack([s["input_ids"] for s in samples])
     else:
-        ids = torch.tensor([s["input_ids"] for s in samples], dtype=torch.long)
+        import numpy as np
+
+        ids = torch.from_numpy(np.stack([np.asarray(s["input_ids"]) for s in samples]))
     return {"input_ids": ids.long()}
 
 
@@ -177,7 +179,9 @@ def load_pretokenized(path: str, seed: int = 0):
     import datasets
 
     dd = datasets.load_from_disk(path)
-    dd.set_format(type="torch", columns=["input_ids"])
+    # plain python rows: the torch / numpy formatters of `datasets` import torchvision (often broken or absent on
+    # training boxes); the collate function turns the id lists into one int64 tensor per batch
+    dd.set_format(type=None, columns=["input_ids"])
     train = dd["train"]
     if seed != 0:
         train = train.shuffle(seed=seed)

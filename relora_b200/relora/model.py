@@ -72,6 +72,10 @@ class ReLoRaModel(nn.Module):
         if r <= 0:
             raise ValueError("r must be positive. If you want r == 0, use the original model.")
         super().__init__()
+        if lora_only and keep_original_weights:
+            # upstream asserts here (relora.py:126-127), which makes plain `--use_peft` without --relora crash;
+            # LoRA-only training has no frozen weight to keep, so the flag is simply dropped
+            keep_original_weights = False
         self.wrapped_model = model
         self.r = r
         self.lora_alpha = lora_alpha
@@ -120,8 +124,6 @@ class ReLoRaModel(nn.Module):
             new.module_index = index
             if keep_original_weights and init_lora_a == "zeros":
                 nn.init.zeros_(new.lora_A.weight)
-            if lora_only:
-                assert not keep_original_weights
             parent_name, _, leaf = name.rpartition(".")
             parent = self.wrapped_model.get_submodule(parent_name) if parent_name else self.wrapped_model
             setattr(parent, leaf, new)

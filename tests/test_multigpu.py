@@ -16,6 +16,10 @@ def _run(mode, nproc=2, port=29641, timeout=420):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), mode]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(log_dir, exist_ok=True)
+    with open(os.path.join(log_dir, f"multigpu_{mode}.log"), "w") as f:
+        f.write(out.stdout + "\n=== stderr ===\n" + out.stderr)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
