@@ -51,7 +51,7 @@ rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
           const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k, int64_t b1_group_kofs,
-          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup) {
+          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias) {
   c10::cuda::CUDAGuard guard(out.device());
   rb::GemmDesc d;
   d.a1 = operand(a1, a1_mn, "a1");
@@ -74,6 +74,11 @@ void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N,
     chk_bf16(*residual, "residual");
     chk_2d_rowmajor(*residual, "residual");
     d.residual = residual->data_ptr(); d.ldr = residual->stride(0);
+  }
+  if (bias.has_value()) {
+    chk_bf16(*bias, "bias");
+    TORCH_CHECK(bias->is_contiguous() && bias->numel() >= N, "bias must be contiguous [N]");
+    d.bias = bias->data_ptr();
   }
   rb::gemm_bf16(d, cur_stream());
 }

@@ -37,6 +37,7 @@ struct GemmDesc {
   bool accumulate = false;  // out += result (fp32 outputs: gradient accumulation)
   const void* residual = nullptr;  // bf16 [M, N], added in fp32 before rounding
   long long ldr = 0;
+  const void* bias = nullptr;      // bf16 [N], added in fp32 (after alpha, before the residual)
   float alpha = 1.0f;
   int block_n = 0;  // 0 = auto, else 128 or 256
   int split_k = 1;  // 1 = off, 0 = auto, >1 = fixed (fp32 accumulate outputs only: partial sums via atomics)

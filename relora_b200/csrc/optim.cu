@@ -69,8 +69,11 @@ void adamw_flat(void* param, const void* grad, bool grad_f32, void* exp_avg, voi
 }
 
 // ============================================================================================ Σ x²
+// Deterministic two-stage reduction (block partials in a fixed order, no atomics): replicas that hold identical
+// gradients must compute bit-identical norms, otherwise their clip coefficients — and then their parameters — drift.
+constexpr int kSumsqBlocks = 1024;
 template <typename T>
-__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, long long n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const T* __restrict__ x, long long n, float* __restrict__ partials) {
   __shared__ float scratch[32];
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -78,13 +81,27 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, lon
     acc += f * f;
   }
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int nb, float* __restrict__ out) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partials[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) *out += acc;
 }
 void sumsq(const void* x, bool is_f32, long long n, float* out, cudaStream_t s) {
-  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 4);
-  if (is_f32) sumsq_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, out);
-  else sumsq_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, n, out);
-  RB_CHECK_LAUNCH("sumsq");
+  static float* partials[16] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (partials[dev & 15] == nullptr) check(cudaMalloc(&partials[dev & 15], kSumsqBlocks * sizeof(float)), "cudaMalloc(sumsq partials)");
+  float* ws = partials[dev & 15];
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)kSumsqBlocks);
+  if (is_f32) sumsq_partial_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, ws);
+  else sumsq_partial_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, n, ws);
+  RB_CHECK_LAUNCH("sumsq_partial");
+  sumsq_final_kernel<<<1, 256, 0, s>>>(ws, grid, out);
+  RB_CHECK_LAUNCH("sumsq_final");
 }
 
 // ============================================================================================ pruning

@@ -83,6 +83,7 @@ def gemm(
     b1_local_n: bool = False,
     m_per_group: int = 0,
     b1_mn_ofs_per_mgroup: int = 0,
+    bias: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """``out[M,N] = alpha·(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)`` on the tcgen05 kernel.
 
@@ -104,7 +105,7 @@ def gemm(
         assert not accumulate
     _C().gemm(a1, b1, out, M, N, K1, a2, b2, K2, a1_mn, b1_mn, n_per_group, a1_group_kofs, a2_group_kofs,
               residual, float(alpha), accumulate, block_n, split_k, b1_group_kofs, b1_local_n, m_per_group,
-              b1_mn_ofs_per_mgroup)
+              b1_mn_ofs_per_mgroup, bias)
     return out
 
 
@@ -157,7 +158,7 @@ class _LoRALinearFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, lora_a, lora_b, scale, p, key, training):
+    def forward(ctx, x, weight, lora_a, lora_b, scale, p, key, training, bias=None):
         C = _C()
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
@@ -173,7 +174,8 @@ class _LoRALinearFn(torch.autograd.Function):
         else:
             xd = x2
         u = gemm(xd, lora_a, alpha=scale)  # [M, r]
-        y = gemm(x2, weight, a2=u, b2=lora_b, K2=r)
+        y = gemm(x2, weight, a2=u, b2=lora_b, K2=r, bias=bias)  # bias (Pythia) is added in the GEMM epilogue
+        ctx.has_bias = bias is not None
         ctx.save_for_backward(x2, weight, lora_a, lora_b, u)
         ctx.meta = (scale, p if drop else 0.0, key, shp)
         # the seed tensor is advanced once per micro-step *after* backward, so backward re-derives the mask
@@ -210,13 +212,14 @@ class _LoRALinearFn(torch.autograd.Function):
         db = torch.zeros(N, r, dtype=torch.float32, device=x2.device)
         # u already carries the factor s (u = s·xd·Aᵀ), and dB = s·dyᵀ·(xd·Aᵀ) = dyᵀ·u
         gemm(dy2, u, db, M=N, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0)
-        return dx.reshape(shp), None, da.to(lora_a.dtype), db.to(lora_b.dtype), None, None, None, None
+        dbias = dy2.float().sum(0).to(dy2.dtype) if ctx.has_bias else None
+        return dx.reshape(shp), None, da.to(lora_a.dtype), db.to(lora_b.dtype), None, None, None, None, dbias
 
 
 def relora_linear_module(module, x: torch.Tensor) -> torch.Tensor:
     """Fused forward for a :class:`ReLoRaLinear` (falls back to PyTorch for the unsupported corners)."""
     unsupported = (
-        module.lora_only or module.bias is not None or module.trainable_scaling or module.quantize is not None
+        module.lora_only or module.trainable_scaling or module.quantize is not None
         or module.in_features % 8 or module.out_features % 8 or module.r % 8
     )
     if unsupported:
@@ -227,7 +230,7 @@ def relora_linear_module(module, x: torch.Tensor) -> torch.Tensor:
         out = F.linear(x, module.weight, module.bias)
         return out + module.lora_B(module.lora_A(module.lora_dropout(x))) * module._post_lora_scale()
     return _LoRALinearFn.apply(x, module.weight, module.lora_A.weight, module.lora_B.weight, float(module.scaling),
-                               float(module.lora_dropout.p), int(module.module_index) + 1, module.training)
+                               float(module.lora_dropout.p), int(module.module_index) + 1, module.training, module.bias)
 
 
 # ----------------------------------------------------------------------------- LM head + cross entropy
