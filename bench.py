@@ -323,9 +323,35 @@ def run_reference(args):
     dist.destroy_process_group()
 
 
+class _QuietStdout:
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr so that stdout carries exactly
+    the one JSON line of the bench contract."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        real = os.fdopen(os.dup(self._saved), "w")
+        self._print = builtins_print = print
+
+        def emit(*a, **k):
+            builtins_print(*a, **dict(k, file=real, flush=True))
+
+        globals()["print"] = emit
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        globals().pop("print", None)
+        return False
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    with _QuietStdout():
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)

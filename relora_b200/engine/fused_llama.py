@@ -51,8 +51,9 @@ def supports(model, args=None) -> Tuple[bool, str]:
     h, f, nh = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
     r = model.r
     hd = h // nh
-    if h % 128 or f % 128 or r % 128:
-        return False, f"hidden ({h}), intermediate ({f}) and rank ({r}) must be multiples of 128 for stacked groups"
+    if h % 128 or r % 128:
+        # the intermediate size may be anything (llama_1b: 5461): its buffers are zero-padded to a multiple of 128
+        return False, f"hidden ({h}) and rank ({r}) must be multiples of 128 for stacked groups"
     if hd % 8 or hd % 4:
         return False, "head_dim must be a multiple of 8"
     p = next(inner.parameters())
@@ -69,13 +70,14 @@ class _Layer:
 
     __slots__ = ("Wqkv", "Wo", "Wgu", "Wd", "A_qkv", "B_qkv", "A_o", "B_o", "A_gu", "B_gu", "A_d", "B_d", "w1", "w2",
                  "gA_qkv", "gB_qkv", "gA_o", "gB_o", "gA_gu", "gB_gu", "gA_d", "gB_d", "gw1", "gw2", "keys_qkv", "key_o",
-                 "keys_gu", "key_d", "mods")
+                 "keys_gu", "key_d", "mods", "merge")
 
 
 class FusedLlamaStepper:
     def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
-                 transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096):
+                 transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096,
+                 overlap_wgrad: bool = True):
         ok, why = supports(model)
         if not ok:
             raise RuntimeError(why)
@@ -89,6 +91,7 @@ class FusedLlamaStepper:
         cfg = self.inner.config
         self.h, self.f, self.nh, self.V = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.vocab_size
         self.hd = self.h // self.nh
+        self.fp = (self.f + 127) // 128 * 128  # padded intermediate size (zero rows / columns)
         self.r = model.r
         self.L = cfg.num_hidden_layers
         self.eps = cfg.rms_norm_eps
@@ -99,11 +102,11 @@ class FusedLlamaStepper:
 
         # ---------------------------------------------------------------- stacked frozen weights
         dev = self.device
-        h, f, r, L = self.h, self.f, self.r, self.L
+        h, f, fp, r, L = self.h, self.f, self.fp, self.r, self.L
         self.Wqkv = torch.empty(L, 3 * h, h, dtype=BF, device=dev)
         self.Wo = torch.empty(L, h, h, dtype=BF, device=dev)
-        self.Wgu = torch.empty(L, 2 * f, h, dtype=BF, device=dev)
-        self.Wd = torch.empty(L, h, f, dtype=BF, device=dev)
+        self.Wgu = torch.zeros(L, 2 * fp, h, dtype=BF, device=dev)
+        self.Wd = torch.zeros(L, h, fp, dtype=BF, device=dev)
         layers = self.inner.model.layers
         with torch.no_grad():
             for l, layer in enumerate(layers):
@@ -112,8 +115,8 @@ class FusedLlamaStepper:
                     self._rehome(m.weight, self.Wqkv[l, j * h:(j + 1) * h])
                 self._rehome(at.o_proj.weight, self.Wo[l])
                 self._rehome(mlp.gate_proj.weight, self.Wgu[l, :f])
-                self._rehome(mlp.up_proj.weight, self.Wgu[l, f:])
-                self._rehome(mlp.down_proj.weight, self.Wd[l])
+                self._rehome(mlp.up_proj.weight, self.Wgu[l, fp:fp + f])
+                self._rehome(mlp.down_proj.weight, self.Wd[l][:, :f])
 
         # ---------------------------------------------------------------- flat trainable store (stack-friendly order)
         named: List[Tuple[str, torch.nn.Parameter]] = []
@@ -156,15 +159,24 @@ class FusedLlamaStepper:
                     logger.warning(f"peer-memory collectives unavailable ({type(e).__name__}: {e}); using NCCL")
             elif transport == "p2p":
                 raise RuntimeError("--comm p2p needs torch symmetric memory over an NCCL process group")
+        padded: Dict[int, Tuple[int, int]] = {}
+        if fp != f:
+            for layer in layers:
+                mlp = layer.mlp
+                padded[id(mlp.gate_proj.lora_B.weight)] = (fp, r)
+                padded[id(mlp.up_proj.lora_B.weight)] = (fp, r)
+                padded[id(mlp.down_proj.lora_A.weight)] = (r, fp)
         self.store = FlatParamStore(named, world_size=info.world_size, grad_dtype=torch.float32, bind_grads=False,
-                                    allocator=self.comm.allocator() if self.comm is not None else None)
+                                    allocator=self.comm.allocator() if self.comm is not None else None,
+                                    storage_shapes=padded)
         self.trainable_params = [p for _, p in named]
         self.trainable_names = [n for n, _ in named]
         self.lora_params = [p for n, p in named if "lora_" in n]
 
         def pv(p, rows_mult=1):  # stacked view over `rows_mult` adjacent parameters (params and grads)
             o, n = self.store.segment(p)
-            shape = (p.shape[0] * rows_mult, p.shape[1]) if p.dim() == 2 else (p.shape[0] * rows_mult,)
+            ps = self.store.storage.get(id(p), tuple(p.shape))  # padded block shape where one exists
+            shape = (ps[0] * rows_mult, ps[1]) if p.dim() == 2 else (ps[0] * rows_mult,)
             tot = n * rows_mult
             return self.store.params[o:o + tot].view(shape), self.store.grads[o:o + tot].view(shape)
 
@@ -191,7 +203,11 @@ class FusedLlamaStepper:
             S.mods = (at.q_proj, at.k_proj, at.v_proj, at.o_proj, mlp.gate_proj, mlp.up_proj, mlp.down_proj)
             # sanity: the stacked views must alias the module parameters
             assert S.A_qkv[r:2 * r].data_ptr() == at.k_proj.lora_A.weight.data_ptr()
-            assert S.B_gu[f:].data_ptr() == mlp.up_proj.lora_B.weight.data_ptr()
+            assert S.B_gu[fp:].data_ptr() == mlp.up_proj.lora_B.weight.data_ptr()
+            assert S.A_d.data_ptr() == mlp.down_proj.lora_A.weight.data_ptr() and S.A_d.shape == (r, fp)
+            # (B, A, W) blocks of the merge GEMM  W += s·B·A  (padded blocks where the module views are strided)
+            S.merge = [(m.lora_B.weight.data, m.lora_A.weight.data, m.weight.data) for m in S.mods[:4]]
+            S.merge += [(S.B_gu[:fp], S.A_gu[:r], S.Wgu[:fp]), (S.B_gu[fp:], S.A_gu[r:], S.Wgu[fp:]), (S.B_d, S.A_d, S.Wd)]
             self.layers.append(S)
         emb = self.inner.model.embed_tokens
         self.W_emb, self.gW_emb = pv(emb.weight)
@@ -223,6 +239,8 @@ class FusedLlamaStepper:
         self._replays = 0
         self._launches_per_micro = 0
         self._attn_saved: List = []
+        self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
+        self._wg_done: Dict[str, torch.cuda.Event] = {}
 
     # ------------------------------------------------------------------ plumbing
     @staticmethod
@@ -231,7 +249,7 @@ class FusedLlamaStepper:
         param.data = dst
 
     def _alloc(self, B: int, T: int):
-        dev, h, f, r, L = self.device, self.h, self.f, self.r, self.L
+        dev, h, f, r, L = self.device, self.h, self.fp, self.r, self.L  # f: padded intermediate size
         M = B * T
         e = lambda *s: torch.empty(*s, dtype=BF, device=dev)  # noqa: E731
         self.B_, self.T_, self.M_ = B, T, M
@@ -263,7 +281,7 @@ class FusedLlamaStepper:
         self.dqkv = e(M, 3 * h)
         self.dgu = e(M, 2 * f)
         self.dhmid, self.dhmid2 = e(M, f), e(M, f)
-        self.du = e(M, 3 * r)
+        self.du_bufs = {"d": e(M, r), "gu": e(M, 2 * r), "o": e(M, r), "qkv": e(M, 3 * r)}
         self.parts = e(M, max(3 * h, f))
         ldv = (self.V + 7) // 8 * 8
         self.logits = torch.zeros(min(self.ce_chunk, M), ldv, dtype=BF, device=dev)
@@ -294,7 +312,7 @@ class FusedLlamaStepper:
         g(xn, W, out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=residual)
 
     def _forward(self, train: bool):
-        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.f, self.r
+        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.fp, self.r
         p = self.p if train else 0.0
         seed = self.seed
         C.embedding_fwd(self.ids.view(-1), self.W_emb, self.x_in[0])
@@ -367,33 +385,56 @@ class FusedLlamaStepper:
                 g(lg, hc, self.gW_head, M=V, N=h, K1=m, a1_mn=True, b1_mn=True, accumulate=True)
         torch.div(self.loss_sum[0], float(n_valid), out=self.loss_out)
 
-    def _lora_group_bwd(self, dy, S_B, S_W, S_A, gA, gB, xd, u, keys, *, G, K, Ng, base_out, out):
-        """Backward of one stacked LoRA group.  dy [M, G·Ng] -> out [M, K] (grad of the group's input)."""
+    def _lora_group_bwd(self, dy, S_B, S_W, S_A, gA, gB, xd, u, keys, *, G, K, Ng, base_out, out, tag):
+        """Backward of one stacked LoRA group.  dy [M, G·Ng] -> out [M, K] (grad of the group's input).
+
+        The two weight-gradient GEMMs only read (dy, du, xd, u), so they are forked onto a side stream and fill the
+        SMs that the skinny du / parts GEMMs and kernel tails of the main chain leave idle; ``self._wg_done[tag]``
+        is the event the main stream waits on before it overwrites one of their inputs (see ``_backward``)."""
         C, g, M, r, s = self.C, fused.gemm, self.M_, self.r, self.scale
-        du = self.du[:, :G * r] if G * r == self.du.shape[1] else self.du.view(-1)[: M * G * r].view(M, G * r)
+        du = self.du_bufs[tag]
         # du_g = s · dy_g · B_g          (B stacked [G·Ng, r], read MN-major; K window g·Ng)
         g(dy, S_B, du, M=M, N=G * r, K1=Ng, b1_mn=True, n_per_group=r, a1_group_kofs=Ng if G > 1 else 0,
           b1_group_kofs=Ng if G > 1 else 0, b1_local_n=True, alpha=s)
+        drop = self.p > 0
+        shared_x = (not drop) or xd.shape[1] != G * K
+
+        def wgrads():  # fp32, accumulated across micro-batches, split-K over tokens
+            g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+              m_per_group=r if G > 1 else 0, b1_mn_ofs_per_mgroup=0 if shared_x else K)
+            g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+              m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0)
+
+        if self.side is not None:
+            fork = torch.cuda.Event()
+            fork.record()
+            self.side.wait_event(fork)
+            with torch.cuda.stream(self.side):
+                wgrads()
+                done = torch.cuda.Event()
+                done.record()
+            self._wg_done[tag] = done
         # frozen path: base = dy · W     (W stacked [G·Ng, K], read MN-major)
         g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
         # low-rank path per group: part_g = du_g · A_g
         parts = self.parts.view(-1)[: M * G * K].view(M, G * K)
         g(du, S_A, parts, M=M, N=G * K, K1=r, b1_mn=True, n_per_group=K, a1_group_kofs=r if G > 1 else 0,
           b1_group_kofs=r if G > 1 else 0, b1_local_n=True)
-        drop = self.p > 0
         if drop:
             C.dropout_combine(base_out, parts, out, self.seed, keys, self.p)
         else:
             torch.add(base_out, parts.view(M, G, K).sum(1) if G > 1 else parts, out=out)
-        # weight gradients (fp32, accumulated across micro-batches, split-K over tokens)
-        shared_x = (not drop) or xd.shape[1] != G * K
-        g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
-          m_per_group=r if G > 1 else 0, b1_mn_ofs_per_mgroup=0 if shared_x else K)
-        g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
-          m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0)
+        if self.side is None:
+            wgrads()
+
+    def _join(self, tag):
+        """Main stream waits for the side-stream weight gradients tagged ``tag`` (no-op if none are pending)."""
+        ev = self._wg_done.pop(tag, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def _backward(self):
-        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.f, self.r
+        C, g, M, h, f, r = self.C, fused.gemm, self.M_, self.h, self.fp, self.r
         B, T, nh, hd = self.B_, self.T_, self.nh, self.hd
         dx, dx_other = self.dx_a, self.dx_b
         ws, tk = fused.norm_workspace(self.device, h)
@@ -402,17 +443,20 @@ class FusedLlamaStepper:
             S = self.layers[l]
             # ---- MLP: x_next = hmid·Wdᵀ + u_d·B_dᵀ + x1
             self._lora_group_bwd(dx, S.B_d, S.Wd, S.A_d, S.gA_d, S.gB_d, self.xd_d[l], self.u_d[l], [S.key_d],
-                                 G=1, K=f, Ng=h, base_out=self.dhmid, out=self.dhmid2)
+                                 G=1, K=f, Ng=h, base_out=self.dhmid, out=self.dhmid2, tag="d")
+            self._join("gu")  # the previous layer's gate/up weight gradients read dgu / du_gu
             C.swiglu_bwd(self.dhmid2, self.gu[l], self.dgu)
             self._lora_group_bwd(self.dgu, S.B_gu, S.Wgu, S.A_gu, S.gA_gu, S.gB_gu, self.xd_gu[l], self.u_gu[l], S.keys_gu,
-                                 G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2)
+                                 G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2, tag="gu")
+            self._join("o")  # ... and its o_proj weight gradients read the buffer this norm backward writes
             C.rmsnorm_bwd(self.dxn2, self.x1[l], S.w2, self.rstd2[l], dx, dx_other, S.gw2, ws, tk)
             dx, dx_other = dx_other, dx  # dx = grad wrt x1
             # ---- attention: x1 = attn·Woᵀ + u_o·B_oᵀ + x
             self._lora_group_bwd(dx, S.B_o, S.Wo, S.A_o, S.gA_o, S.gB_o, self.xd_o[l], self.u_o[l], [S.key_o],
-                                 G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn)
+                                 G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn, tag="o")
             o, q, k, v = self._attn_saved[l]
             dq, dk, dv = torch.autograd.grad(o, (q, k, v), self.dattn.view(B, T, nh, hd).transpose(1, 2))
+            self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
             if dq.stride() == dk.stride() == dv.stride() and dq.stride(3) == 1:
                 C.rope_pack_bwd(dq, dk, dv, self.dqkv, hd, self.cos, self.sin, 0)  # gather + inverse rotation in one pass
             else:
@@ -420,10 +464,13 @@ class FusedLlamaStepper:
                 d5[:, :, 0].copy_(dq.transpose(1, 2)); d5[:, :, 1].copy_(dk.transpose(1, 2)); d5[:, :, 2].copy_(dv.transpose(1, 2))
                 C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)
             self._lora_group_bwd(self.dqkv, S.B_qkv, S.Wqkv, S.A_qkv, S.gA_qkv, S.gB_qkv, self.xd_qkv[l], self.u_qkv[l],
-                                 S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2)
+                                 S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2, tag="qkv")
+            self._join("d")  # this layer's down_proj weight gradients read the buffer written next
             C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1, ws, tk)
             dx, dx_other = dx_other, dx
         C.embedding_bwd(self.ids.view(-1), dx, self.gW_emb, self.pad_idx)
+        for tag in ("d", "gu", "o", "qkv"):
+            self._join(tag)
         self._attn_saved.clear()
 
     def _micro_body(self):
@@ -537,9 +584,8 @@ class FusedLlamaStepper:
 
         g, r = fused.gemm, self.r
         for S in self.layers:
-            for m in S.mods:
-                g(m.lora_B.weight.data, m.lora_A.weight.data, m.weight.data, M=m.out_features, N=m.in_features, K1=r,
-                  b1_mn=True, alpha=self.scale, accumulate=True)
+            for m, (Bm, Am, Wm) in zip(S.mods, S.merge):
+                g(Bm, Am, Wm, M=Wm.shape[0], N=Wm.shape[1], K1=r, b1_mn=True, alpha=self.scale, accumulate=True)
                 sd = ref.mix_seed(self.model.seed, self.model.n_restarts, m.module_index)
                 self.C.fill_uniform_hash(m.lora_A.weight.data, sd, 1.0 / math.sqrt(m.in_features))
                 m.lora_B.weight.data.zero_()

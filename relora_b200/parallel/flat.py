@@ -46,6 +46,7 @@ class FlatParamStore:
         allocator: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
         bind_grads: bool = True,
         grad_allocator: Optional[Callable[[int, torch.dtype, torch.device], torch.Tensor]] = None,
+        storage_shapes: Optional[Dict[int, Tuple[int, int]]] = None,
     ):
         if not named_params:
             raise ValueError("no trainable parameters")
@@ -56,11 +57,19 @@ class FlatParamStore:
         for n, p in named_params:
             if p.dtype != self.dtype or p.device != self.device:
                 raise ValueError(f"parameter {n} has dtype/device {p.dtype}/{p.device}, expected {self.dtype}/{self.device}")
+        # optional padded storage: a 2-D parameter [R, C] may live in a larger [R_s, C_s] block (row stride C_s) so that
+        # stacked / TMA-aligned views exist; the padding stays exactly zero (zero gradients, zero moments)
+        self.storage: Dict[int, Tuple[int, int]] = dict(storage_shapes or {})
+        for p in self.param_list:
+            if id(p) in self.storage:
+                rs, cs = self.storage[id(p)]
+                if p.dim() != 2 or rs < p.shape[0] or cs < p.shape[1]:
+                    raise ValueError("storage shape must cover the 2-D parameter")
         self.offsets: List[int] = []
         off = 0
         for p in self.param_list:
             self.offsets.append(off)
-            off += _round_up(p.numel(), _ALIGN)
+            off += _round_up(self._storage_numel(p), _ALIGN)
         self.used = off
         self.numel = _round_up(off, _ALIGN * max(1, world_size))
         alloc = allocator or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
@@ -72,29 +81,50 @@ class FlatParamStore:
         # gradients themselves (fp32 accumulation for bf16 parameters) keep the views to themselves
         self.bind_grads = bind_grads and self.grad_dtype == self.dtype
         with torch.no_grad():
-            for p, o in zip(self.param_list, self.offsets):
-                view = self.params[o : o + p.numel()].view(p.shape)
+            self.index: Dict[int, int] = {id(p): i for i, p in enumerate(self.param_list)}
+            for p in self.param_list:
+                view = self.view_like(self.params, p)
                 view.copy_(p.data)
                 p.data = view
                 if self.bind_grads:
-                    p.grad = self.grads[o : o + p.numel()].view(p.shape)
-        self.index: Dict[int, int] = {id(p): i for i, p in enumerate(self.param_list)}
+                    p.grad = self.view_like(self.grads, p)
 
     # ------------------------------------------------------------------ views
+    def _storage_numel(self, p: torch.nn.Parameter) -> int:
+        st = self.storage.get(id(p))
+        return p.numel() if st is None else st[0] * st[1]
+
+    def is_padded(self, p: torch.nn.Parameter) -> bool:
+        return id(p) in self.storage
+
     def segment(self, p: torch.nn.Parameter) -> Tuple[int, int]:
+        """(offset, number of *storage* elements) of ``p`` in the flat buffers."""
         i = self.index[id(p)]
-        return self.offsets[i], self.param_list[i].numel()
+        return self.offsets[i], self._storage_numel(self.param_list[i])
 
     def view_like(self, flat: torch.Tensor, p: torch.nn.Parameter, base: int = 0) -> torch.Tensor:
+        """View of ``flat`` shaped like ``p`` (a strided slice of the padded block for padded parameters)."""
         o, n = self.segment(p)
-        return flat[o - base : o - base + n].view(p.shape)
+        st = self.storage.get(id(p))
+        if st is None:
+            return flat[o - base : o - base + n].view(p.shape)
+        return flat[o - base : o - base + n].view(st[0], st[1])[: p.shape[0], : p.shape[1]]
+
+    def to_storage(self, p: torch.nn.Parameter, value: torch.Tensor) -> torch.Tensor:
+        """``value`` (shaped like ``p``) laid out as the flat storage segment of ``p`` (zero padded)."""
+        st = self.storage.get(id(p))
+        if st is None:
+            return value.reshape(-1)
+        full = torch.zeros(st[0], st[1], dtype=value.dtype, device=value.device)
+        full[: p.shape[0], : p.shape[1]] = value
+        return full.reshape(-1)
 
     def rebind_grads(self) -> None:
         """Point every ``.grad`` back at its flat view (after ``zero_grad(set_to_none=True)`` etc.)."""
         if not self.bind_grads:
             return
-        for p, o in zip(self.param_list, self.offsets):
-            p.grad = self.grads[o : o + p.numel()].view(p.shape)
+        for p in self.param_list:
+            p.grad = self.view_like(self.grads, p)
 
     def zero_grads(self) -> None:
         self.grads.zero_()
@@ -157,8 +187,8 @@ class FlatAdamW(torch.optim.Optimizer):
             if o >= lo and o + n <= hi:
                 self.state[p] = {
                     "step": self._step_t,
-                    "exp_avg": self.exp_avg[o - lo : o - lo + n].view(p.shape),
-                    "exp_avg_sq": self.exp_avg_sq[o - lo : o - lo + n].view(p.shape),
+                    "exp_avg": self.store.view_like(self.exp_avg, p, base=lo),
+                    "exp_avg_sq": self.store.view_like(self.exp_avg_sq, p, base=lo),
                 }
 
     def consolidate_state_dict(self, to: int = 0) -> None:
@@ -182,7 +212,7 @@ class FlatAdamW(torch.optim.Optimizer):
             self.state.clear()
             for p in self.store.param_list:
                 o, n = self.store.segment(p)
-                self.state[p] = {"step": self._step_t, "exp_avg": full_m[o : o + n].view(p.shape), "exp_avg_sq": full_v[o : o + n].view(p.shape)}
+                self.state[p] = {"step": self._step_t, "exp_avg": self.store.view_like(full_m, p), "exp_avg_sq": self.store.view_like(full_v, p)}
             out = super().state_dict()
             self.state.clear()
             self.state.update(saved)
@@ -204,8 +234,8 @@ class FlatAdamW(torch.optim.Optimizer):
             o, n = self.store.segment(p)
             a, b = max(o, lo), min(o + n, hi)
             if a < b:
-                self.exp_avg[a - lo : b - lo].copy_(st["exp_avg"].reshape(-1)[a - o : b - o])
-                self.exp_avg_sq[a - lo : b - lo].copy_(st["exp_avg_sq"].reshape(-1)[a - o : b - o])
+                self.exp_avg[a - lo : b - lo].copy_(self.store.to_storage(p, st["exp_avg"])[a - o : b - o])
+                self.exp_avg_sq[a - lo : b - lo].copy_(self.store.to_storage(p, st["exp_avg_sq"])[a - o : b - o])
             s = st.get("step")
             if s is not None:
                 step_val = float(s.item() if torch.is_tensor(s) else s)
@@ -276,11 +306,16 @@ class FlatAdamW(torch.optim.Optimizer):
                 else:
                     if self.is_sharded and (a != o or b != o + n):
                         # the tensor straddles a shard boundary: take the quantile over the whole tensor
-                        full = self._gathered(key)[o : o + n]
+                        full = self.store.view_like(self._gathered(key), p)
                         from ..relora.optim_reset import magnitude_threshold
 
                         thr = magnitude_threshold(full, ratio)
                         seg.mul_((seg.abs() > thr).to(seg.dtype))
+                    elif self.store.is_padded(p):
+                        # quantile over the logical tensor only (the zero padding must not shift it)
+                        from ..relora.optim_reset import magnitude_pruning_
+
+                        magnitude_pruning_(self.store.view_like(bufs[key], p, base=lo), ratio)
                     elif self._native is not None and seg.is_cuda:
                         self._native.magnitude_prune_(seg, ratio)
                     else:

@@ -15,11 +15,11 @@ def _relerr(a, b):
     return float((a - b).norm() / b.norm().clamp(min=1e-12))
 
 
-def _build(p_drop, seed=0):
+def _build(p_drop, seed=0, inter=512):
     from relora_b200.models import LlamaForCausalLM, SimpleConfig
     from relora_b200.relora import ReLoRaModel
 
-    cfg = SimpleConfig(model_type="llama", vocab_size=4096, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+    cfg = SimpleConfig(model_type="llama", vocab_size=4096, hidden_size=256, intermediate_size=inter, num_hidden_layers=2,
                        num_attention_heads=4, rms_norm_eps=1e-6, pad_token_id=-1, max_position_embeddings=256)
     torch.manual_seed(seed)
     m = LlamaForCausalLM(cfg)
@@ -35,15 +35,16 @@ def _info():
     return DistInfo(0, 0, 1, torch.device("cuda", 0), "nccl")
 
 
-@pytest.mark.parametrize("p_drop", [0.0, 0.1])
-@pytest.mark.parametrize("graphs", [False, True])
-def test_fused_matches_module_path(p_drop, graphs):
+@pytest.mark.parametrize("p_drop,graphs,inter", [(0.0, False, 512), (0.1, False, 512), (0.0, True, 512), (0.1, True, 512),
+                                                  (0.1, True, 341), (0.0, False, 341)])
+def test_fused_matches_module_path(p_drop, graphs, inter):
+    """``inter=341`` exercises the zero-padded MLP blocks used for llama_1b (intermediate 5461 -> 5504)."""
     from relora_b200.engine.fused_llama import FusedLlamaStepper
     from relora_b200.engine.stepper import ModuleStepper
     from relora_b200.ops import fused
 
     dev = torch.device("cuda", 0)
-    wa = _build(p_drop)
+    wa = _build(p_drop, inter=inter)
     wb = copy.deepcopy(wa)
     ids = torch.randint(0, 4096, (3, 64), device=dev)
     fs = FusedLlamaStepper(wa, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=graphs)
@@ -74,11 +75,12 @@ def test_fused_matches_module_path(p_drop, graphs):
     assert torch.isfinite(ev) and abs(float(ev) - float(l2)) < 0.5
 
 
-def test_fused_merge_and_checkpoint_roundtrip(tmp_path):
+@pytest.mark.parametrize("inter", [512, 341])
+def test_fused_merge_and_checkpoint_roundtrip(tmp_path, inter):
     from relora_b200.engine.fused_llama import FusedLlamaStepper
     from relora_b200.relora import ReLoRaModel
 
-    w = _build(0.1)
+    w = _build(0.1, inter=inter)
     fs = FusedLlamaStepper(w, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=False)
     ids = torch.randint(0, 4096, (2, 64), device="cuda")
     w.eval()
@@ -88,6 +90,8 @@ def test_fused_merge_and_checkpoint_roundtrip(tmp_path):
     fs.merge_and_reinit()
     assert _relerr(q.weight, want) < 4e-3
     assert float(q.lora_B.weight.abs().sum()) == 0
+    dn = w.wrapped_model.model.layers[1].mlp.down_proj
+    assert dn.weight.shape == (256, inter) and float(dn.lora_A.weight.abs().sum()) > 0
     after = fs.eval_loss(ids)
     assert abs(float(before) - float(after)) < 3e-2
     # parameters are views of the stacked buffers, checkpoints still have the reference layout
