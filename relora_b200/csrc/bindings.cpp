@@ -165,6 +165,33 @@ void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, co
                       (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 
+// out[M,N] = dy[M,Kb]·W[Kb,N] + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)     (fused input gradient of a stacked LoRA group)
+void lora_dx(const Tensor& dy, const Tensor& w, const Tensor& du, const Tensor& a, Tensor& out, const OptTensor& seed,
+             std::vector<int64_t> keys, double p) {
+  chk_bf16(dy, "dy"); chk_bf16(w, "w"); chk_bf16(du, "du"); chk_bf16(a, "a"); chk_bf16(out, "out");
+  chk_2d_rowmajor(dy, "dy"); chk_2d_rowmajor(w, "w"); chk_2d_rowmajor(du, "du"); chk_2d_rowmajor(a, "a"); chk_2d_rowmajor(out, "out");
+  const int G = (int)keys.size();
+  TORCH_CHECK(G >= 1 && G <= 3, "lora_dx: 1..3 groups");
+  rb::LoraDxDesc d;
+  d.M = (int)dy.size(0); d.Kb = (int)dy.size(1); d.N = (int)w.size(1); d.groups = G;
+  TORCH_CHECK(w.size(0) == d.Kb, "w must be [Kb, N]");
+  TORCH_CHECK(du.size(0) == d.M && du.size(1) % G == 0, "du must be [M, G*r]");
+  d.r = (int)(du.size(1) / G);
+  TORCH_CHECK(a.size(0) == du.size(1) && a.size(1) == d.N, "a must be [G*r, N]");
+  TORCH_CHECK(out.size(0) == d.M && out.size(1) == d.N, "out must be [M, N]");
+  d.dy = dy.data_ptr(); d.ld_dy = dy.stride(0);
+  d.w = w.data_ptr(); d.ld_w = w.stride(0);
+  d.du = du.data_ptr(); d.ld_du = du.stride(0);
+  d.a = a.data_ptr(); d.ld_a = a.stride(0);
+  d.out = out.data_ptr(); d.ldc = out.stride(0);
+  d.drop_threshold24 = (uint32_t)llround(p * 16777216.0);
+  d.inv_keep = (float)(1.0 / (1.0 - p));
+  d.seed_ptr = u32ptr(seed);
+  for (int i = 0; i < G; ++i) d.seed_key[i] = (uint32_t)keys[i];
+  c10::cuda::CUDAGuard guard(out.device());
+  rb::lora_dx(d, cur_stream());
+}
+
 void rope_inplace(Tensor& buf, int64_t T, int64_t n_rot_heads, int64_t hd, int64_t rotary_dim, const Tensor& cos, const Tensor& sin,
                   bool backward, int64_t pos0) {
   chk_bf16(buf, "buf"); chk_bf16(cos, "cos"); chk_bf16(sin, "sin");
@@ -354,6 +381,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
   m.def("dropout_expand", &dropout_expand);
   m.def("dropout_combine", &dropout_combine);
+  m.def("lora_dx", &lora_dx);
   m.def("rope_inplace", &rope_inplace);
   m.def("rope_pack_bwd", &rope_pack_bwd);
   m.def("swiglu_fwd", &swiglu_fwd);

@@ -163,16 +163,27 @@ __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restr
   const uint32_t base = seed_ptr ? *seed_ptr : 0u;
   const uint32_t seeds[4] = {mix_seed(base, keys.x), mix_seed(base, keys.y), mix_seed(base, keys.z), mix_seed(base, keys.w)};
   const int hv = H / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / hv;
-    const int c = int(i % hv);
-    float f[8];
-    unpack8(reinterpret_cast<const bf16x8*>(x)[i], f);
-    for (int g = 0; g < G; ++g) {
-      float d[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // two independent 16-byte loads in flight per thread (a single one leaves HBM half idle, Little's law)
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n_vec; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool has1 = i1 < n_vec;
+    const bf16x8 v0 = reinterpret_cast<const bf16x8*>(x)[i0];
+    const bf16x8 v1 = has1 ? reinterpret_cast<const bf16x8*>(x)[i1] : v0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24) ? f[j] * inv_keep : 0.f;
-      reinterpret_cast<bf16x8*>(xd + (row * G + g) * H)[c] = pack8(d);
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const long long i = u ? i1 : i0;
+      const long long row = i / hv;
+      const int c = int(i % hv);
+      float f[8];
+      unpack8(u ? v1 : v0, f);
+      for (int g = 0; g < G; ++g) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24) ? f[j] * inv_keep : 0.f;
+        reinterpret_cast<bf16x8*>(xd + (row * G + g) * H)[c] = pack8(d);
+      }
     }
   }
 }
@@ -264,19 +275,44 @@ void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd
 }
 
 // ============================================================================================ SwiGLU
+// h = silu(gate) * up ; optionally also hd = keep ⊙ h / (1-p) (the dropout-expanded copy the LoRA down-projection of
+// down_proj consumes) so that h is not re-read by a separate dropout kernel.  Two vectors in flight per thread.
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ldgu, bf16* __restrict__ h, long long ldh,
-                                                         int M, int F) {
+                                                         int M, int F, bf16* __restrict__ hd, long long ldhd,
+                                                         const uint32_t* __restrict__ seed_ptr, uint32_t key, uint32_t thr24, float inv_keep) {
   const int fv = F / 8;
   const long long total = (long long)M * fv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / fv;
-    const int c = int(i % fv) * 8;
-    float g[8], u[8], o[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + row * ldgu + c), g);
-    unpack8(*reinterpret_cast<const bf16x8*>(gu + row * ldgu + F + c), u);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint32_t seed = hd != nullptr ? mix_seed(seed_ptr ? *seed_ptr : 0u, key) : 0u;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool has1 = i1 < total;
+    const long long r0 = i0 / fv, r1 = has1 ? i1 / fv : r0;
+    const int c0 = int(i0 % fv) * 8, c1 = has1 ? int(i1 % fv) * 8 : c0;
+    const bf16x8 g0 = *reinterpret_cast<const bf16x8*>(gu + r0 * ldgu + c0);
+    const bf16x8 u0 = *reinterpret_cast<const bf16x8*>(gu + r0 * ldgu + F + c0);
+    const bf16x8 g1 = *reinterpret_cast<const bf16x8*>(gu + r1 * ldgu + c1);
+    const bf16x8 u1 = *reinterpret_cast<const bf16x8*>(gu + r1 * ldgu + F + c1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
-    *reinterpret_cast<bf16x8*>(h + row * ldh + c) = pack8(o);
+    for (int t = 0; t < 2; ++t) {
+      if (t == 1 && !has1) break;
+      const long long row = t ? r1 : r0;
+      const int c = t ? c1 : c0;
+      float g[8], u[8], o[8];
+      unpack8(t ? g1 : g0, g);
+      unpack8(t ? u1 : u0, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
+      const bf16x8 packed = pack8(o);
+      *reinterpret_cast<bf16x8*>(h + row * ldh + c) = packed;
+      if (hd != nullptr) {
+        float ob[8], d[8];
+        unpack8(packed, ob);  // the mask multiplies the rounded activation, exactly like dropout_expand(h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = keep_bit(seed, (uint32_t)row, (uint32_t)(c + j), thr24) ? ob[j] * inv_keep : 0.f;
+        *reinterpret_cast<bf16x8*>(hd + row * ldhd + c) = pack8(d);
+      }
+    }
   }
 }
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ gu,
@@ -301,11 +337,12 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
     *reinterpret_cast<bf16x8*>(dgu + row * lddgu + F + c) = pack8(du);
   }
 }
-void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, cudaStream_t s) {
-  if (F % 8 || ldgu % 8 || ldh % 8) throw std::runtime_error("swiglu: F and leading dims must be multiples of 8");
+void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, void* hd, long long ldhd,
+                const uint32_t* seed_ptr, uint32_t key, uint32_t thr24, float inv_keep, cudaStream_t s) {
+  if (F % 8 || ldgu % 8 || ldh % 8 || (hd != nullptr && ldhd % 8)) throw std::runtime_error("swiglu: F and leading dims must be multiples of 8");
   const long long total = (long long)M * (F / 8);
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-  swiglu_fwd_kernel<<<grid, 256, 0, s>>>((const bf16*)gu, ldgu, (bf16*)h, ldh, M, F);
+  const int grid = (int)std::min<long long>((total + 511) / 512, (long long)num_sms() * 8);
+  swiglu_fwd_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>((const bf16*)gu, ldgu, (bf16*)h, ldh, M, F, (bf16*)hd, ldhd, seed_ptr, key, thr24, inv_keep);
   RB_CHECK_LAUNCH("swiglu_fwd");
 }
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,

@@ -54,6 +54,23 @@ struct GemmDesc {
 
 void gemm_bf16(const GemmDesc& d, cudaStream_t stream);
 
+// Input gradient of a stacked LoRA group with the dropout mask applied in the epilogue:
+//   out[M,N] = dy[M,Kb]·W[Kb,N] + inv_keep · Σ_g keep(seed_g; row, col) ⊙ (du_g[M,r]·A_g[r,N]),  g < groups <= 3
+// dy/du are K-major activations (du = [du_0 | du_1 | ...]); W [Kb, N] and A = [A_0; A_1; ...] ([groups·r, N]) are the
+// parameters as stored (read MN-major in place).  seed_g = mix_seed(*seed_ptr, seed_key[g]).
+struct LoraDxDesc {
+  const void *dy = nullptr, *w = nullptr, *du = nullptr, *a = nullptr;
+  long long ld_dy = 0, ld_w = 0, ld_du = 0, ld_a = 0;
+  void* out = nullptr;
+  long long ldc = 0;
+  int M = 0, N = 0, Kb = 0, r = 0, groups = 1;
+  uint32_t drop_threshold24 = 0;  // 0 = keep everything (no dropout)
+  float inv_keep = 1.0f;
+  const uint32_t* seed_ptr = nullptr;
+  uint32_t seed_key[3] = {0, 0, 0};
+};
+void lora_dx(const LoraDxDesc& d, cudaStream_t stream);
+
 // Drop cached TMA descriptors (call when buffers are freed / reallocated).
 void gemm_clear_descriptor_cache();
 

@@ -47,7 +47,9 @@ struct KernelArgs {
   float alpha;
   int out_f32, accumulate;
   int num_m_tiles, num_n_tiles;
+  int tiles_per_group;  // N-tiles per output-column group (the last one of a group may be ragged)
   int use_tma_store;  // bf16 output written through swizzled smem slabs + TMA store
+  int res_tma;        // ... and the residual is fetched into the same slab by TMA (coalesced) instead of per-row loads
   int split_k;  // >1: each output tile is computed by split_k CTAs over disjoint K ranges, combined with fp32 atomics
 };
 
@@ -99,7 +101,7 @@ template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
-            const __grid_constant__ CUtensorMap map_out, const KernelArgs p) {
+            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const KernelArgs p) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (256 or 512 columns)
@@ -110,7 +112,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;  // residual slab landed (TMA load into the output slab, see epilogue)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -123,6 +126,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       tma_prefetch_desc(&map_b2);
     }
     if (p.use_tma_store) tma_prefetch_desc(&map_out);
+    if (p.res_tma) tma_prefetch_desc(&map_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -132,6 +136,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&res_bar[a], 1);
     }
     fence_barrier_init();
   }
@@ -159,12 +164,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
         const int tile = work / p.split_k, split = work % p.split_k;
         const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-        const int g = n0 / p.n_per_group;
+        const int tn = tile % p.num_n_tiles;
+        const int g = tn / p.tiles_per_group;
+        const int nl = (tn % p.tiles_per_group) * BLOCK_N;  // column offset inside the group
+        const int n0 = g * p.n_per_group + nl;
         const int a1_k = g * p.a1_group_kofs;
         const int a2_k = g * p.a2_group_kofs;
         const int b1_k = g * p.b1_group_kofs;
-        const int b1_n = (p.b1_local_n ? n0 - g * p.n_per_group : n0) + (m0 / p.m_per_group) * p.b1_mn_ofs_per_mgroup;
+        const int b1_n = (p.b1_local_n ? nl : n0) + (m0 / p.m_per_group) * p.b1_mn_ofs_per_mgroup;
         const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -242,10 +249,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     const bool res_vec = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const bool out_vec = (p.ldc % (p.out_f32 ? 4 : 8) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int slab_counter = 0;
+    // residual slabs travel by TMA into the (swizzled) output slab one slab ahead of their use; each thread then
+    // reads back exactly the 16-byte chunks it is about to overwrite
+    auto slab_coords = [&](int work_i, int sl_i, int& c_col, int& c_row) {
+      const int tile_i = work_i / p.split_k;
+      const int tn_i = tile_i % p.num_n_tiles;
+      c_row = (tile_i / p.num_n_tiles) * BLOCK_M;
+      c_col = (tn_i / p.tiles_per_group) * p.n_per_group + (tn_i % p.tiles_per_group) * BLOCK_N + sl_i * 64;
+    };
+    if (p.res_tma && issuer && (int)blockIdx.x < num_work) {
+      int c_col, c_row;
+      slab_coords(blockIdx.x, 0, c_col, c_row);
+      mbar_arrive_expect_tx(&res_bar[0], L::kSlabBytes);
+      tma_load_2d(&map_res, &res_bar[0], stage_base, c_col, c_row, kEvictNormal);
+    }
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int tile = work / p.split_k, split = work % p.split_k;
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const int tn = tile % p.num_n_tiles;
+      const int nl = (tn % p.tiles_per_group) * BLOCK_N;
+      const int n0 = (tn / p.tiles_per_group) * p.n_per_group + nl;
+      const int n_lim = min(p.N, n0 + min(BLOCK_N, p.n_per_group - nl));  // a group's last tile may be ragged
       const bool empty_split = split * kb_per_split >= num_kb;  // nothing was accumulated for this work item
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -265,8 +289,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         if (p.use_tma_store) {
           // ---- (a) bf16 via swizzled smem + TMA store
           uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
-          if (issuer) tma_store_wait_read<1>();  // the store that used this slab two slabs ago has drained
-          named_bar_sync(1, 128);
+          const uint32_t rloc = quad * 32 + lane;
+          uint8_t* rowp = slab + rloc * 128;
+          if (p.res_tma) {
+            mbar_wait(&res_bar[slab_counter & 1], (slab_counter >> 1) & 1);  // residual slab landed (slab was free before the load)
+          } else {
+            if (issuer) tma_store_wait_read<1>();  // the store that used this slab two slabs ago has drained
+            named_bar_sync(1, 128);
+          }
           uint4 packed[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -276,10 +306,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
               f[i] = __uint_as_float(raw) * p.alpha;
             }
-            add_bias8(p.bias, col0 + q * 8, p.N, f);
-            if (p.residual != nullptr && row_ok) {
+            add_bias8(p.bias, col0 + q * 8, n_lim, f);
+            if (p.res_tma) {
+              float a[8];
+              unpack8(*reinterpret_cast<const uint4*>(rowp + ((q ^ (rloc & 7)) << 4)), a);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += a[i];
+            } else if (p.residual != nullptr && row_ok) {
               const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
-              if (res_vec && col0 + q * 8 + 8 <= p.N) {
+              if (res_vec && col0 + q * 8 + 8 <= n_lim) {
                 float a[8];
                 unpack8(*reinterpret_cast<const uint4*>(rp), a);
 #pragma unroll
@@ -287,23 +322,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  if (col0 + q * 8 + i < p.N) f[i] += __bfloat162float(rp[i]);
+                  if (col0 + q * 8 + i < n_lim) f[i] += __bfloat162float(rp[i]);
               }
             }
             packed[q] = pack8(f);
           }
-          const uint32_t rloc = quad * 32 + lane;
-          uint8_t* rowp = slab + rloc * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (issuer && !empty_split) {
+          if (issuer && !empty_split && col0 < n_lim) {
             tma_store_2d(&map_out, slab, col0, m0);
             tma_store_commit();
           }
+          if (p.res_tma && issuer) {  // prefetch the next slab's residual into the other buffer
+            int nwork = work, nsl = sl + 1;
+            if (nsl == BLOCK_N / 64) {
+              nsl = 0;
+              nwork = work + gridDim.x;
+            }
+            if (nwork < num_work) {
+              int c_col, c_row;
+              slab_coords(nwork, nsl, c_col, c_row);
+              tma_store_wait_read<1>();  // every store but the one just committed has read its slab: the other buffer is free
+              const int nb = (slab_counter + 1) & 1;
+              mbar_arrive_expect_tx(&res_bar[nb], L::kSlabBytes);
+              tma_load_2d(&map_res, &res_bar[nb], stage_base + nb * L::kSlabBytes, c_col, c_row, kEvictNormal);
+            }
+          }
           ++slab_counter;
-        } else if (row_ok && !empty_split && col0 < p.N) {
+        } else if (row_ok && !empty_split && col0 < n_lim) {
           // ---- (b) direct global path
           if (p.split_k > 1) {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
@@ -313,14 +361,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
               const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
               const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
-              if (out_vec && col0 + q * 4 + 4 <= p.N) {  // one 16-byte vector reduction instead of four scalar atomics
+              if (out_vec && col0 + q * 4 + 4 <= n_lim) {  // one 16-byte vector reduction instead of four scalar atomics
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + q * 4), "f"(a0), "f"(a1), "f"(a2), "f"(a3)
                              : "memory");
               } else {
                 const float e[4] = {a0, a1, a2, a3};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (col0 + q * 4 + i < p.N) atomicAdd(op + q * 4 + i, e[i]);
+                  if (col0 + q * 4 + i < n_lim) atomicAdd(op + q * 4 + i, e[i]);
               }
             }
           } else if (p.out_f32) {
@@ -332,7 +380,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
               o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
               o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
-              if (out_vec && col0 + q * 4 + 4 <= p.N) {
+              if (out_vec && col0 + q * 4 + 4 <= n_lim) {
                 if (p.accumulate) {
                   const float4 old = *reinterpret_cast<const float4*>(op + q * 4);
                   o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -342,7 +390,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
                 const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (col0 + q * 4 + i < p.N) op[q * 4 + i] = p.accumulate ? op[q * 4 + i] + e[i] : e[i];
+                  if (col0 + q * 4 + i < n_lim) op[q * 4 + i] = p.accumulate ? op[q * 4 + i] + e[i] : e[i];
               }
             }
           } else {
@@ -352,8 +400,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(q < 4 ? r0[q * 8 + i] : r1[(q - 4) * 8 + i]) * p.alpha;
-              const bool fullv = col0 + q * 8 + 8 <= p.N;
-              add_bias8(p.bias, col0 + q * 8, p.N, f);
+              const bool fullv = col0 + q * 8 + 8 <= n_lim;
+              add_bias8(p.bias, col0 + q * 8, n_lim, f);
               if (p.residual != nullptr) {
                 const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
                 if (res_vec && fullv) {
@@ -364,7 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
                 } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i)
-                    if (col0 + q * 8 + i < p.N) f[i] += __bfloat162float(rp[i]);
+                    if (col0 + q * 8 + i < n_lim) f[i] += __bfloat162float(rp[i]);
                 }
               }
               if (out_vec && fullv) {
@@ -378,7 +426,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  if (col0 + q * 8 + i < p.N) {
+                  if (col0 + q * 8 + i < n_lim) {
                     const float o = p.accumulate ? __bfloat162float(op[q * 8 + i]) + f[i] : f[i];
                     op[q * 8 + i] = __float2bfloat16_rn(o);
                   }
@@ -393,6 +441,272 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       }
     }
     if (p.use_tma_store && issuer) tma_store_wait<0>();  // all output bytes are globally visible before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// Fused backward of a stacked LoRA group (input gradient):
+//
+//   dx[M,N] = dy[M,Kb] · W[Kb,N]  +  inv_keep · Σ_g keep_g(row, col) ⊙ ( du_g[M,r] · A_g[r,N] )
+//
+// (Kb = G·Ng: the group's stacked output width; N: the group's input width.)  The dropout mask sits on the LoRA
+// *input*, i.e. on the output of this backward product, so the low-rank terms cannot share the accumulator of the
+// frozen path.  Each CTA therefore keeps 1+G accumulators per tile in tensor memory: the G short LoRA products are
+// issued first, and while the long frozen-path reduction runs on the tensor core the epilogue warps already read
+// the LoRA accumulators, evaluate the counter-based masks and hold the combined term packed in registers.  This
+// replaces base-GEMM + parts-GEMM + dropout_combine (two extra [M, (G+1)·N] round trips through HBM).
+// Reference math: backward of relora.py:319-322 with nn.Dropout on the LoRA input.
+struct LoraDxArgs {
+  int M, N, Kb, r;
+  int num_m_tiles, num_n_tiles;
+  uint32_t thr24;
+  float inv_keep;
+  const uint32_t* seed_ptr;
+  uint32_t keys[3];
+};
+
+template <int G>
+__global__ void __launch_bounds__(kNumThreads, 1)
+lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_a,
+               const __grid_constant__ CUtensorMap map_out, const LoraDxArgs p) {
+  constexpr int BLOCK_N = 128;
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int kBaseStages = (G <= 2) ? 2 : 1;  // TMEM budget: (kBaseStages + kLoraStages·G) · 128 <= 512 columns
+  constexpr int kLoraStages = (G == 1) ? 2 : 1;
+  constexpr uint32_t kTmemCols = 512;
+  static_assert((kBaseStages + kLoraStages * G) * BLOCK_N <= 512, "tensor memory budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* lora_full = empty_bar + kStages;
+  uint64_t* lora_empty = lora_full + 2;
+  uint64_t* base_full = lora_empty + 2;
+  uint64_t* base_empty = base_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(base_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_du);
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&lora_full[a], 1);
+      mbar_init(&lora_empty[a], 128);
+      mbar_init(&base_full[a], 1);
+      mbar_init(&base_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_lora = p.r / BLOCK_K;                     // r is a multiple of 64
+  const int kb_base = (p.Kb + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < G * kb_lora; ++kb) {  // du [M, G·r] K-major ; A [G·r, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          load_operand<BLOCK_M, false>(&map_du, &full_bar[stage], sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_a, &full_bar[stage], sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          advance();
+        }
+        for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          load_operand<BLOCK_M, false>(&map_dy, &full_bar[stage], sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_w, &full_bar[stage], sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ls = 0, bs = 0;
+      uint32_t ls_phase = 0, bs_phase = 0;
+      auto mma_block = [&](uint32_t d_tmem, bool first) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(first && k == 0));
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&lora_empty[ls], ls_phase ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g) {
+          const uint32_t d_tmem = tmem_base + (kBaseStages + ls * G + g) * BLOCK_N;
+          for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
+        }
+        umma_commit(&lora_full[ls]);
+        mbar_wait(&base_empty[bs], bs_phase ^ 1);
+        tc_fence_after();
+        {
+          const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
+          for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
+        }
+        umma_commit(&base_full[bs]);
+        if (++ls == kLoraStages) {
+          ls = 0;
+          ls_phase ^= 1;
+        }
+        if (++bs == kBaseStages) {
+          bs = 0;
+          bs_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================================================================== epilogue
+    const uint32_t quad = warp & 3;
+    const uint32_t et = threadIdx.x - kEpilogueWarp0 * 32;
+    const bool issuer = (et == 0);
+    uint8_t* stage_base = smem + L::kTileBytes + L::kBarrierBytes;
+    const uint32_t seed0 = p.seed_ptr ? *p.seed_ptr : 0u;
+    uint32_t seeds[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) seeds[g] = mix_seed(seed0, p.keys[g]);
+    int ls = 0, bs = 0;
+    uint32_t ls_phase = 0, bs_phase = 0;
+    int slab_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const uint32_t row = m0 + quad * 32 + lane;
+      const uint32_t rowmix = row * 0x9E3779B1u;
+      // ---- phase 1: masked sum of the LoRA accumulators, packed to bf16x2 (overlaps the frozen-path MMAs)
+      uint32_t cpk[BLOCK_N / 2];
+      mbar_wait(&lora_full[ls], ls_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < BLOCK_N / 16; ++ch) {
+        float cf[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf[i] = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          uint32_t rr[16];
+          tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + ch * 16), rr);
+          tmem_ld_wait();
+          const uint32_t sg = rowmix ^ seeds[g];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t col = (uint32_t)(n0 + ch * 16 + i);
+            const uint32_t hsh = lowbias32(sg ^ (col * 0x85EBCA77u));
+            if ((hsh >> 8) >= p.thr24) cf[i] += __uint_as_float(rr[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cpk[ch * 8 + i] = pack_bf16x2(cf[2 * i] * p.inv_keep, cf[2 * i + 1] * p.inv_keep);
+      }
+      tc_fence_before();
+      mbar_arrive(&lora_empty[ls]);
+      // ---- phase 2: frozen-path accumulator + combined LoRA term -> bf16 slab -> TMA store
+      mbar_wait(&base_full[bs], bs_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int sl = 0; sl < BLOCK_N / 64; ++sl) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64), r0);
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64 + 32), r1);
+        tmem_ld_wait();
+        if (sl == BLOCK_N / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(&base_empty[bs]);
+        }
+        uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint4 packed[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
+            const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+            const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+            const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
+            f[i] = __uint_as_float(raw0) + c2.x;
+            f[i + 1] = __uint_as_float(raw1) + c2.y;
+          }
+          packed[q] = pack8(f);
+        }
+        const uint32_t rloc = quad * 32 + lane;
+        uint8_t* rowp = slab + rloc * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&map_out, slab, n0 + sl * 64, m0);
+          tma_store_commit();
+        }
+        ++slab_counter;
+      }
+      if (++ls == kLoraStages) {
+        ls = 0;
+        ls_phase ^= 1;
+      }
+      if (++bs == kBaseStages) {
+        bs = 0;
+        bs_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -490,9 +804,12 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   if (d.bias != nullptr && d.out_f32) throw std::runtime_error("gemm: bias is only fused for bf16 outputs");
   p.alpha = d.alpha; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
   p.num_m_tiles = ceil_div(d.M, BLOCK_M);
-  p.num_n_tiles = ceil_div(d.N, BLOCK_N);
   const int groups = ceil_div(d.N, p.n_per_group);
-  if (groups > 1 && (p.n_per_group % BLOCK_N) != 0) throw std::runtime_error("gemm: n_per_group must be a multiple of BLOCK_N");
+  // tiles never straddle a group: the last tile of a group may be ragged (its tail columns are computed but not
+  // stored), which is what lets llama_1b's 5504-wide gate/up groups run with 256-wide tiles
+  if (groups > 1 && (p.n_per_group % 64) != 0) throw std::runtime_error("gemm: n_per_group must be a multiple of 64");
+  p.tiles_per_group = ceil_div(p.n_per_group, BLOCK_N);
+  p.num_n_tiles = groups * p.tiles_per_group;
 
   // K extents of the global tensors include the per-group windows
   const long long a1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.a1_group_kofs;
@@ -533,9 +850,11 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   if (grid <= 0) return;
   p.use_tma_store = (!d.out_f32 && !d.accumulate && split == 1 && (d.ldc % 8 == 0) &&
                      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0) ? 1 : 0;
-  CUtensorMap mout = ma1;
+  CUtensorMap mout = ma1, mres = ma1;
   if (p.use_tma_store) mout = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, p);
+  p.res_tma = (p.use_tma_store && d.residual != nullptr && (d.ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) ? 1 : 0;
+  if (p.res_tma) mres = make_map_2d(d.residual, d.N, d.M, d.ldr, 64, BLOCK_M);
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, mres, p);
   RB_CHECK_LAUNCH("gemm_kernel");
 }
 
@@ -558,11 +877,48 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
     // wide tiles halve the shared-memory bandwidth per MMA; keep 128 when the group size demands it or N is small
     const int npg = d.n_per_group > 0 ? d.n_per_group : d.N;
     // (measured on B200, M = 12288: N=768 K=768 27 -> 23 us, N=768 K=2560 64 -> 49 us, N=2304 K=768 64 -> 45 us)
-    const bool groups_ok = (npg % 256 == 0) || (npg >= d.N);
+    const bool groups_ok = (npg % 256 == 0) || (npg >= d.N) || (npg % 64 == 0 && npg >= 2048);  // ragged last tile: <= 6 % waste
     bn = (d.N >= 512 && groups_ok && ceil_div(d.M, BLOCK_M) * ceil_div(d.N, 256) >= num_sms() / 2) ? 256 : 128;
   }
   if (bn == 256) dispatch_major<256>(d, stream);
   else dispatch_major<128>(d, stream);
+}
+
+template <int G>
+static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
+  using L = SmemLayout<128>;
+  LoraDxArgs p;
+  p.M = d.M; p.N = d.N; p.Kb = d.Kb; p.r = d.r;
+  p.num_m_tiles = ceil_div(d.M, BLOCK_M);
+  p.num_n_tiles = ceil_div(d.N, 128);
+  p.thr24 = d.drop_threshold24; p.inv_keep = d.inv_keep; p.seed_ptr = d.seed_ptr;
+  for (int g = 0; g < 3; ++g) p.keys[g] = d.seed_key[g];
+  CUtensorMap m_dy = make_map_2d(d.dy, d.Kb, d.M, d.ld_dy, BLOCK_K, BLOCK_M);
+  CUtensorMap m_w = make_map_2d(d.w, d.N, d.Kb, d.ld_w, 64, BLOCK_K);
+  CUtensorMap m_du = make_map_2d(d.du, (long long)G * d.r, d.M, d.ld_du, BLOCK_K, BLOCK_M);
+  CUtensorMap m_a = make_map_2d(d.a, d.N, (long long)G * d.r, d.ld_a, 64, BLOCK_K);
+  CUtensorMap m_out = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
+  auto kern = lora_dx_kernel<G>;
+  static bool configured = false;
+  if (!configured) {
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(lora_dx)");
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return;
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(m_dy, m_w, m_du, m_a, m_out, p);
+  RB_CHECK_LAUNCH("lora_dx_kernel");
+}
+
+void lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0) return;
+  if (d.groups < 1 || d.groups > 3) throw std::runtime_error("lora_dx: 1..3 stacked LoRA groups");
+  if (d.r <= 0 || d.r % BLOCK_K != 0) throw std::runtime_error("lora_dx: the LoRA rank must be a multiple of 64");
+  if (d.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) throw std::runtime_error("lora_dx: output must be 16-byte aligned");
+  if (d.groups == 1) launch_lora_dx<1>(d, stream);
+  else if (d.groups == 2) launch_lora_dx<2>(d, stream);
+  else launch_lora_dx<3>(d, stream);
 }
 
 }  // namespace rb

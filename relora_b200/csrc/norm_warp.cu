@@ -201,8 +201,23 @@ bool rmsnorm_bwd_warp(const void* dy, const void* x, const void* w, const float*
   const int vpl = pick_vpl(H / 8);
   (void)ws; (void)ticket;  // kept in the signature for the workspace-based variant; dw now uses vector reductions
   if (vpl == 0 || (reinterpret_cast<uintptr_t>(dw) & 15) != 0) return false;
-  const int grid = std::min(ceil_div(M, kWarpsPerBlock), 4 * num_sms());
   const size_t smem = (size_t)H * sizeof(float);
+  // exactly one resident wave: a second wave would pay the per-block prologue / dw reduction again for ~2 rows per warp
+  static int occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (occ[vpl] == 0) {
+    int n = 0;
+#define O(V) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rmsnorm_bwd_warp_kernel<V>, kWarpsPerBlock * 32, smem)
+    switch (vpl) {
+      case 1: O(1); break;
+      case 2: O(2); break;
+      case 3: O(3); break;
+      case 4: O(4); break;
+      default: O(8); break;
+    }
+#undef O
+    occ[vpl] = n > 0 ? n : 1;
+  }
+  const int grid = std::min(ceil_div(M, kWarpsPerBlock), occ[vpl] * num_sms());
   const bf16 *a = (const bf16*)dy, *b = (const bf16*)x, *c = (const bf16*)w, *d = (const bf16*)dx_add;
 #define L(V) rmsnorm_bwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, smem, s>>>(a, b, c, rstd, d, (bf16*)dx, dw, M, H)
   switch (vpl) {

@@ -22,6 +22,7 @@ with the module-by-module PyTorch path on identical weights and masks.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -240,6 +241,7 @@ class FusedLlamaStepper:
         self._launches_per_micro = 0
         self._attn_saved: List = []
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
+        self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
         self._wg_done: Dict[str, torch.cuda.Event] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -414,16 +416,20 @@ class FusedLlamaStepper:
                 done = torch.cuda.Event()
                 done.record()
             self._wg_done[tag] = done
-        # frozen path: base = dy · W     (W stacked [G·Ng, K], read MN-major)
-        g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
-        # low-rank path per group: part_g = du_g · A_g
-        parts = self.parts.view(-1)[: M * G * K].view(M, G * K)
-        g(du, S_A, parts, M=M, N=G * K, K1=r, b1_mn=True, n_per_group=K, a1_group_kofs=r if G > 1 else 0,
-          b1_group_kofs=r if G > 1 else 0, b1_local_n=True)
-        if drop:
-            C.dropout_combine(base_out, parts, out, self.seed, keys, self.p)
+        if self.fused_dx:
+            # one kernel: out = dy·W + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)  (1+G accumulators in tensor memory, masks in the epilogue)
+            C.lora_dx(dy, S_W, du, S_A, out, self.seed if drop else None, list(keys) if drop else [0] * G, self.p if drop else 0.0)
         else:
-            torch.add(base_out, parts.view(M, G, K).sum(1) if G > 1 else parts, out=out)
+            # frozen path: base = dy · W     (W stacked [G·Ng, K], read MN-major)
+            g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
+            # low-rank path per group: part_g = du_g · A_g
+            parts = self.parts.view(-1)[: M * G * K].view(M, G * K)
+            g(du, S_A, parts, M=M, N=G * K, K1=r, b1_mn=True, n_per_group=K, a1_group_kofs=r if G > 1 else 0,
+              b1_group_kofs=r if G > 1 else 0, b1_local_n=True)
+            if drop:
+                C.dropout_combine(base_out, parts, out, self.seed, keys, self.p)
+            else:
+                torch.add(base_out, parts.view(M, G, K).sum(1) if G > 1 else parts, out=out)
         if self.side is None:
             wgrads()
 

@@ -228,7 +228,19 @@ def relora_linear_module(module, x: torch.Tensor) -> torch.Tensor:
         if module.lora_only:
             return module.lora_B(module.lora_A(module.lora_dropout(x))) * module._post_lora_scale()
         out = F.linear(x, module.weight, module.bias)
-        return out + module.lora_B(module.lora_A(module.lora_dropout(x))) * module._post_lora_scale()
+        pd = float(module.lora_dropout.p) if module.training else 0.0
+        xd = x
+        if pd > 0.0 and x.is_cuda:
+            # same counter-based mask as the kernels (shapes the TMA path cannot take, e.g. llama_1b's 5461-wide MLP)
+            from . import reference as ref
+
+            base = int(seed_state.get(x.device).item()) & 0xFFFFFFFF
+            x2 = x.reshape(-1, x.shape[-1])
+            keep = ref.dropout_keep_mask(ref.mix_seed(base, int(module.module_index) + 1), x2.shape[0], x2.shape[1], pd, device=x.device)
+            xd = (x2 * keep.to(x.dtype) * (1.0 / (1.0 - pd))).reshape(x.shape).to(x.dtype)
+        elif pd > 0.0:
+            xd = module.lora_dropout(x)
+        return out + module.lora_B(module.lora_A(xd)) * module._post_lora_scale()
     return _LoRALinearFn.apply(x, module.weight, module.lora_A.weight, module.lora_B.weight, float(module.scaling),
                                float(module.lora_dropout.p), int(module.module_index) + 1, module.training, module.bias)
 

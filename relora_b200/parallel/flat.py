@@ -74,6 +74,7 @@ class FlatParamStore:
         self.numel = _round_up(off, _ALIGN * max(1, world_size))
         alloc = allocator or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
         self.params = alloc(self.numel, self.dtype, self.device)
+        self.params.zero_()  # alignment gaps and padded blocks must be exactly zero (custom allocators may not clear)
         self.grad_dtype = grad_dtype or self.dtype
         galloc = grad_allocator or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
         self.grads = galloc(self.numel, self.grad_dtype, self.device)

@@ -122,6 +122,34 @@ def test_gemm_many_tiles_persistent(F):
     assert _relerr(out2, a.float() @ b.float().t()) < 6e-3
 
 
+@pytest.mark.parametrize("G,Ng,K,M,p", [(1, 256, 256, 300, 0.1), (2, 384, 256, 512, 0.1), (3, 256, 384, 1000, 0.1), (3, 128, 128, 128, 0.0),
+                                        (1, 256, 640, 20000, 0.25), (2, 5504, 2048, 256, 0.1)])
+def test_lora_dx_fused_dropout_epilogue(C, G, Ng, K, M, p):
+    """dx = dy·W + Σ_g keep_g ⊙ (du_g·A_g)/(1-p): 1+G tensor-memory accumulators, masks evaluated in the epilogue."""
+    from relora_b200.ops import reference as ref
+
+    r = 128
+    torch.manual_seed(G * 7 + M)
+    dy, W = _rand(M, G * Ng), _rand(G * Ng, K, scale=0.05)
+    du, A = _rand(M, G * r), _rand(G * r, K, scale=0.05)
+    seed = torch.tensor([1234567], dtype=torch.int32, device="cuda")
+    keys = [11, 22, 33][:G]
+    out = torch.empty(M, K, dtype=BF, device="cuda")
+    C.lora_dx(dy, W, du, A, out, seed if p > 0 else None, keys, p)
+    want = dy.float() @ W.float()
+    for g in range(G):
+        part = du[:, g * r:(g + 1) * r].float() @ A[g * r:(g + 1) * r].float()
+        if p > 0:
+            keep = ref.dropout_keep_mask(ref.mix_seed(1234567, keys[g]), M, K, p, device="cuda")
+            part = part * keep / (1.0 - p)
+        want = want + part
+    assert _relerr(out, want) < 6e-3
+    # the mask really is applied per group: without it the result differs by O(p)
+    if p > 0:
+        nomask = dy.float() @ W.float() + du.float() @ A.float() / (1.0 - p)
+        assert _relerr(out, nomask) > 1e-2
+
+
 # ----------------------------------------------------------------------------------------- elementwise
 @pytest.mark.parametrize("M,H", [(64, 768), (300, 2048), (17, 4096), (5, 128)])
 def test_rmsnorm_fwd_bwd(C, M, H):
