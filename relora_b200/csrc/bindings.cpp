@@ -51,9 +51,10 @@ rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
           const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k, int64_t b1_group_kofs,
-          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias) {
+          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias, int64_t cta_pair) {
   c10::cuda::CUDAGuard guard(out.device());
   rb::GemmDesc d;
+  d.cta_pair = (int)cta_pair;
   d.a1 = operand(a1, a1_mn, "a1");
   d.b1 = operand(b1, b1_mn, "b1");
   d.M = (int)M; d.N = (int)N; d.K1 = (int)K1; d.K2 = (int)K2;
@@ -216,12 +217,20 @@ void rope_pack_bwd(const Tensor& dq, const Tensor& dk, const Tensor& dv, Tensor&
                     hd, (int)rotary_dim, cos.data_ptr(), sin.data_ptr(), (int)pos0, cur_stream());
 }
 
-void swiglu_fwd(const Tensor& gu, Tensor& h) {
+void swiglu_fwd(const Tensor& gu, Tensor& h, const OptTensor& hd, const OptTensor& seed, int64_t key, double p) {
   chk_bf16(gu, "gu"); chk_bf16(h, "h"); chk_2d_rowmajor(gu, "gu"); chk_2d_rowmajor(h, "h");
   const int F = (int)h.size(1);
   TORCH_CHECK(gu.size(1) == 2 * F && gu.size(0) == h.size(0));
+  void* hdp = nullptr;
+  long long ldhd = 0;
+  if (hd.has_value()) {
+    chk_bf16(*hd, "hd"); chk_2d_rowmajor(*hd, "hd");
+    TORCH_CHECK(hd->size(0) == h.size(0) && hd->size(1) == F, "hd must be [M, F]");
+    hdp = hd->data_ptr(); ldhd = hd->stride(0);
+  }
   c10::cuda::CUDAGuard guard(gu.device());
-  rb::swiglu_fwd(gu.data_ptr(), gu.stride(0), h.data_ptr(), h.stride(0), (int)h.size(0), F, cur_stream());
+  rb::swiglu_fwd(gu.data_ptr(), gu.stride(0), h.data_ptr(), h.stride(0), (int)h.size(0), F, hdp, ldhd, u32ptr(seed), (uint32_t)key,
+                 (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
   chk_bf16(dh, "dh"); chk_bf16(gu, "gu"); chk_bf16(dgu, "dgu");
@@ -384,7 +393,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lora_dx", &lora_dx);
   m.def("rope_inplace", &rope_inplace);
   m.def("rope_pack_bwd", &rope_pack_bwd);
-  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_fwd", &swiglu_fwd, py::arg("gu"), py::arg("h"), py::arg("hd") = py::none(), py::arg("seed") = py::none(),
+        py::arg("key") = 0, py::arg("p") = 0.0);
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd", &embedding_bwd);

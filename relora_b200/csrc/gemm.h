@@ -41,6 +41,7 @@ struct GemmDesc {
   float alpha = 1.0f;
   int block_n = 0;  // 0 = auto, else 128 or 256
   int split_k = 1;  // 1 = off, 0 = auto, >1 = fixed (fp32 accumulate outputs only: partial sums via atomics)
+  int cta_pair = -1; // -1 = auto, 0 = single-CTA tiles, 1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles; needs block_n 256)
   // dropout-combine epilogue (backward of the LoRA branch): if n_lora_acc > 0 the A2/B2 products of
   // the first n_lora_acc K2-windows (each of width lora_r) are kept in separate accumulators and combined as
   //     out = acc0 + sum_g keep_g(row, col) * acc_{1+g} * inv_keep

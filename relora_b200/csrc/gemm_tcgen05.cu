@@ -53,30 +53,42 @@ struct KernelArgs {
   int split_k;  // >1: each output tile is computed by split_k CTAs over disjoint K ranges, combined with fp32 atomics
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // CTA pair: each CTA stages half of the B tile
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 128) ? 5 : 3;
+  static constexpr int kStages = (kStageBytes <= 32768) ? 5 : 3;
   static constexpr int kTileBytes = kStages * kStageBytes;
   static constexpr int kBarrierBytes = 1024;                          // barriers + tmem slot (keeps the slabs 1024-aligned)
   static constexpr int kSlabBytes = BLOCK_M * 128;                    // one 128 x 64 bf16 output slab (128B swizzle)
   static constexpr int kTotal = kTileBytes + kBarrierBytes + 2 * kSlabBytes + 1024;  // +1024 for manual alignment
 };
 
-// Issue the TMA loads of one operand tile (BLOCK_MN x BLOCK_K) into `dst`.
-template <int BLOCK_MN, bool MN_MAJOR>
-__device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int mn0, int k0, uint64_t hint) {
+// Issue the TMA loads of one operand tile (BLOCK_MN x BLOCK_K) into `dst`; `bar` is the 32-bit shared address of the
+// mbarrier (for CTA pairs: the shared::cluster address of the leader's barrier).
+template <int BLOCK_MN, bool MN_MAJOR, bool PAIR = false>
+__device__ __forceinline__ void load_operand(const CUtensorMap* map, uint32_t bar, uint8_t* dst, int mn0, int k0, uint64_t hint) {
+  auto ld = [&](uint8_t* d, int c0, int c1) {
+    if constexpr (PAIR) {
+      tma_load_2d_pair(map, bar, d, c0, c1, hint);
+    } else {
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+          " [%0], [%1, {%3, %4}], [%2], %5;"
+          :
+          : "r"(smem_u32(d)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+          : "memory");
+    }
+  };
   if constexpr (!MN_MAJOR) {
-    tma_load_2d(map, bar, dst, k0, mn0, hint);  // box {64 (K), BLOCK_MN}
+    ld(dst, k0, mn0);  // box {64 (K), BLOCK_MN}
   } else {
 #pragma unroll
-    for (int j = 0; j < BLOCK_MN / 64; ++j)  // box {64 (MN), 64 (K)} = 8 KB each
-      tma_load_2d(map, bar, dst + j * 8192, mn0 + j * 64, k0, hint);
+    for (int j = 0; j < BLOCK_MN / 64; ++j) ld(dst + j * 8192, mn0 + j * 64, k0);  // box {64 (MN), 64 (K)} = 8 KB each
   }
 }
-
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr, int kstep) {
   if constexpr (!MN_MAJOR) return make_desc_sw128(smem_addr + kstep * (UMMA_K * 2), 16, 1024);
@@ -97,14 +109,19 @@ __device__ __forceinline__ void add_bias8(const bf16* bias, int col, int N, floa
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const KernelArgs p) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, PAIR>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (256 or 512 columns)
+  constexpr int kTileM = PAIR ? 2 * BLOCK_M : BLOCK_M;  // rows of the output tile owned by one CTA / CTA pair
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int work0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int work_step = PAIR ? (int)cluster_count_x() : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -135,17 +152,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], PAIR ? 256 : 128);  // pair: the epilogues of both CTAs release the leader's barrier
       mbar_init(&res_bar[a], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_base_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_base_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_base_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -161,9 +184,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const uint32_t full_addr0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      const int b_half = PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0;  // this CTA's share of the B tile
+      for (int work = work0; work < num_work; work += work_step) {
         const int tile = work / p.split_k, split = work % p.split_k;
-        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int m0 = (tile / p.num_n_tiles) * kTileM + (int)cta_rank * BLOCK_M;
         const int tn = tile % p.num_n_tiles;
         const int g = tn / p.tiles_per_group;
         const int nl = (tn % p.tiles_per_group) * BLOCK_N;  // column offset inside the group
@@ -177,14 +202,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          const uint32_t fb = full_addr0 + stage * 8;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * L::kStageBytes);  // both CTAs' bytes land here
           if (kb < kb1) {
-            load_operand<BLOCK_M, A_MN>(&map_a1, &full_bar[stage], sa, m0, a1_k + kb * BLOCK_K, kEvictNormal);
-            load_operand<BLOCK_N, B_MN>(&map_b1, &full_bar[stage], sb, b1_n, b1_k + kb * BLOCK_K, kEvictLast);
+            load_operand<BLOCK_M, A_MN, PAIR>(&map_a1, fb, sa, m0, a1_k + kb * BLOCK_K, kEvictNormal);
+            load_operand<L::kBRows, B_MN, PAIR>(&map_b1, fb, sb, b1_n + b_half, b1_k + kb * BLOCK_K, kEvictLast);
           } else {
             const int k = (kb - kb1) * BLOCK_K;
-            load_operand<BLOCK_M, false>(&map_a2, &full_bar[stage], sa, m0, a2_k + k, kEvictNormal);
-            load_operand<BLOCK_N, false>(&map_b2, &full_bar[stage], sb, n0, k, kEvictLast);
+            load_operand<BLOCK_M, false, PAIR>(&map_a2, fb, sa, m0, a2_k + k, kEvictNormal);
+            load_operand<L::kBRows, false, PAIR>(&map_b2, fb, sb, n0 + b_half, k, kEvictLast);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -195,14 +221,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      constexpr uint32_t idesc2 = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc2 = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_flag) {
+        if constexpr (PAIR) umma_f16_ss_pair(d, da, db, idesc, acc_flag);
+        else umma_f16_ss(d, da, db, idesc, acc_flag);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) umma_commit_pair(bar, 3);
+        else umma_commit(bar);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (int work = work0; work < num_work; work += work_step) {
         const int split = work % p.split_k;
         const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -216,19 +250,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           if (kb < kb1) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc1, ((kb - kb_begin) | k) != 0);
+              mma(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc1, ((kb - kb_begin) | k) != 0);
           } else {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), idesc2, ((kb - kb_begin) | k) != 0);
+              mma(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), idesc2, ((kb - kb_begin) | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue(s)
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -254,18 +288,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     auto slab_coords = [&](int work_i, int sl_i, int& c_col, int& c_row) {
       const int tile_i = work_i / p.split_k;
       const int tn_i = tile_i % p.num_n_tiles;
-      c_row = (tile_i / p.num_n_tiles) * BLOCK_M;
+      c_row = (tile_i / p.num_n_tiles) * kTileM + (int)cta_rank * BLOCK_M;
       c_col = (tn_i / p.tiles_per_group) * p.n_per_group + (tn_i % p.tiles_per_group) * BLOCK_N + sl_i * 64;
     };
-    if (p.res_tma && issuer && (int)blockIdx.x < num_work) {
+    const uint32_t tmem_empty_addr0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    if (p.res_tma && issuer && work0 < num_work) {
       int c_col, c_row;
-      slab_coords(blockIdx.x, 0, c_col, c_row);
+      slab_coords(work0, 0, c_col, c_row);
       mbar_arrive_expect_tx(&res_bar[0], L::kSlabBytes);
       tma_load_2d(&map_res, &res_bar[0], stage_base, c_col, c_row, kEvictNormal);
     }
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += work_step) {
       const int tile = work / p.split_k, split = work % p.split_k;
-      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int m0 = (tile / p.num_n_tiles) * kTileM + (int)cta_rank * BLOCK_M;
       const int tn = tile % p.num_n_tiles;
       const int nl = (tn % p.tiles_per_group) * BLOCK_N;
       const int n0 = (tn / p.tiles_per_group) * p.n_per_group + nl;
@@ -283,7 +318,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         tmem_ld_wait();
         if (sl == BLOCK_N / 64 - 1) {  // accumulator fully read: hand it back to the MMA warp early
           tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[acc]);
+          if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_addr0 + acc * 8);
+          else mbar_arrive(&tmem_empty_bar[acc]);
         }
         const int col0 = n0 + sl * 64;
         if (p.use_tma_store) {
@@ -339,7 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
             int nwork = work, nsl = sl + 1;
             if (nsl == BLOCK_N / 64) {
               nsl = 0;
-              nwork = work + gridDim.x;
+              nwork = work + work_step;
             }
             if (nwork < num_work) {
               int c_col, c_row;
@@ -444,10 +480,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer may still read this CTA's shared memory / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -548,16 +586,16 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_du, &full_bar[stage], sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_a, &full_bar[stage], sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
           advance();
         }
         for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_dy, &full_bar[stage], sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_w, &full_bar[stage], sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          load_operand<BLOCK_M, false>(&map_dy, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_w, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
           advance();
         }
       }
@@ -790,9 +828,10 @@ static CUtensorMap operand_map(const Operand& o, long long mn, long long k, int 
   return make_map_2d(o.ptr, mn, k, o.ld, 64, BLOCK_K);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool PAIR = false>
 static void launch(const GemmDesc& d, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, PAIR>;
+  constexpr int kTileM = PAIR ? 2 * BLOCK_M : BLOCK_M;
   KernelArgs p;
   p.M = d.M; p.N = d.N; p.K1 = d.K1; p.K2 = d.K2;
   p.n_per_group = d.n_per_group > 0 ? d.n_per_group : (d.N > 0 ? d.N : 1);
@@ -803,7 +842,7 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   p.bias = reinterpret_cast<const bf16*>(d.bias);
   if (d.bias != nullptr && d.out_f32) throw std::runtime_error("gemm: bias is only fused for bf16 outputs");
   p.alpha = d.alpha; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
-  p.num_m_tiles = ceil_div(d.M, BLOCK_M);
+  p.num_m_tiles = ceil_div(d.M, kTileM);
   const int groups = ceil_div(d.N, p.n_per_group);
   // tiles never straddle a group: the last tile of a group may be ragged (its tail columns are computed but not
   // stored), which is what lets llama_1b's 5504-wide gate/up groups run with 256-wide tiles
@@ -817,16 +856,16 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   const int mgroups = d.m_per_group > 0 ? ceil_div(d.M, d.m_per_group) : 1;
   const long long b1_mn_total = (d.b1_local_n ? (long long)p.n_per_group : (long long)d.N) + (long long)(mgroups - 1) * d.b1_mn_ofs_per_mgroup;
   const long long b1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.b1_group_kofs;
-  if (d.m_per_group > 0 && (d.m_per_group % BLOCK_M) != 0) throw std::runtime_error("gemm: m_per_group must be a multiple of 128");
-  CUtensorMap mb1 = operand_map(d.b1, b1_mn_total, b1_k_total, BLOCK_N);
+  if (d.m_per_group > 0 && (d.m_per_group % kTileM) != 0) throw std::runtime_error("gemm: m_per_group must be a multiple of the M tile");
+  CUtensorMap mb1 = operand_map(d.b1, b1_mn_total, b1_k_total, L::kBRows);
   CUtensorMap ma2 = ma1, mb2 = mb1;
   if (d.K2 > 0) {
     if (d.a2.mn_major || d.b2.mn_major) throw std::runtime_error("gemm: the LoRA (A2/B2) operands must be K-major");
     const long long a2_k_total = (long long)d.K2 + (long long)(groups - 1) * d.a2_group_kofs;
     ma2 = operand_map(d.a2, d.M, a2_k_total, BLOCK_M);
-    mb2 = operand_map(d.b2, d.N, d.K2, BLOCK_N);
+    mb2 = operand_map(d.b2, d.N, d.K2, L::kBRows);
   }
-  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, PAIR>;
   static bool configured = false;
   if (!configured) {
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(gemm)");
@@ -846,7 +885,25 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   // an MMA with no k-blocks would leave the epilogue waiting: every split must own >= 1 k-block or be skipped
   p.split_k = split;
   const int work = tiles * split;
-  const int grid = work < num_sms() ? work : num_sms();
+  int grid = work < num_sms() ? work : num_sms();
+  if (PAIR) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms() / 2 * 2); qc.blockDim = dim3(kNumThreads); qc.dynamicSmemBytes = L::kTotal;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms() / 2;
+      }
+      max_clusters = n;
+    }
+    grid = 2 * (work < max_clusters ? work : max_clusters);  // one CTA pair per work item
+  }
   if (grid <= 0) return;
   p.use_tma_store = (!d.out_f32 && !d.accumulate && split == 1 && (d.ldc % 8 == 0) &&
                      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0) ? 1 : 0;
@@ -854,18 +911,28 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   if (p.use_tma_store) mout = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
   p.res_tma = (p.use_tma_store && d.residual != nullptr && (d.ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) ? 1 : 0;
   if (p.res_tma) mres = make_map_2d(d.residual, d.N, d.M, d.ldr, 64, BLOCK_M);
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, mres, p);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    check(cudaLaunchKernelEx(&cfg, kern, ma1, mb1, ma2, mb2, mout, mres, p), "cudaLaunchKernelEx(gemm pair)");
+  } else {
+    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, mres, p);
+  }
   RB_CHECK_LAUNCH("gemm_kernel");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 static void dispatch_major(const GemmDesc& d, cudaStream_t s) {
   if (d.a1.mn_major) {
-    if (d.b1.mn_major) launch<BLOCK_N, true, true>(d, s);
-    else launch<BLOCK_N, true, false>(d, s);
+    if (d.b1.mn_major) launch<BLOCK_N, true, true, PAIR>(d, s);
+    else launch<BLOCK_N, true, false, PAIR>(d, s);
   } else {
-    if (d.b1.mn_major) launch<BLOCK_N, false, true>(d, s);
-    else launch<BLOCK_N, false, false>(d, s);
+    if (d.b1.mn_major) launch<BLOCK_N, false, true, PAIR>(d, s);
+    else launch<BLOCK_N, false, false, PAIR>(d, s);
   }
 }
 
@@ -880,8 +947,17 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
     const bool groups_ok = (npg % 256 == 0) || (npg >= d.N) || (npg % 64 == 0 && npg >= 2048);  // ragged last tile: <= 6 % waste
     bn = (d.N >= 512 && groups_ok && ceil_div(d.M, BLOCK_M) * ceil_div(d.N, 256) >= num_sms() / 2) ? 256 : 128;
   }
-  if (bn == 256) dispatch_major<256>(d, stream);
-  else dispatch_major<128>(d, stream);
+  // CTA pairs (cta_group::2, M = 256 per instruction): each CTA stages only half of the B tile, which cuts the
+  // L2 -> shared-memory traffic per FLOP by a third (these GEMMs sit at the ~6.3 KB/clk L2 limit with single CTAs)
+  int pair = d.cta_pair;
+  if (pair < 0) pair = (bn == 256 && d.M >= 512 && (d.m_per_group == 0 || d.m_per_group % 256 == 0)) ? 1 : 0;
+  if (pair && bn != 256) throw std::runtime_error("gemm: CTA pairs need block_n = 256");
+  if (bn == 256) {
+    if (pair) dispatch_major<256, true>(d, stream);
+    else dispatch_major<256>(d, stream);
+  } else {
+    dispatch_major<128>(d, stream);
+  }
 }
 
 template <int G>

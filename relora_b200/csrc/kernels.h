@@ -44,7 +44,9 @@ void rope_pack_bwd(const void* dq, const void* dk, const void* dv, long long sB,
 
 // ---- SwiGLU --------------------------------------------------------------------------------
 // gu: [M, 2F] (gate | up) -> h[M, F] = silu(gate) * up
-void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, cudaStream_t s);
+// optional hd[M, F] = keep(mix(seed, key); row, col) ⊙ h / (1-p): the dropout-expanded copy for the next LoRA down-projection
+void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, void* hd, long long ldhd,
+                const uint32_t* seed_ptr, uint32_t key, uint32_t thr24, float inv_keep, cudaStream_t s);
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,
                 cudaStream_t s);
 

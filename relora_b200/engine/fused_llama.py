@@ -356,11 +356,11 @@ class FusedLlamaStepper:
                 C.rmsnorm_fwd(x1, S.w2, xn, self.rstd2[sl], self.eps, None, None, [], 0.0)
                 xd = xn
             self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f)
-            C.swiglu_fwd(gu, self.hmid)
             if p > 0:
                 xd_d = self.xd_d[sl]
-                C.dropout_expand(self.hmid, xd_d, seed, [S.key_d], p)
+                C.swiglu_fwd(gu, self.hmid, xd_d, seed, S.key_d, p)  # activation + its dropout-expanded copy in one pass
             else:
+                C.swiglu_fwd(gu, self.hmid)
                 xd_d = self.hmid
                 if train:
                     self.xd_d[sl].copy_(self.hmid)

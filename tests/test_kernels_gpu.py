@@ -78,6 +78,64 @@ def test_gemm_fused_lora_groups(F, G, Ng, K, r, block_n):
     assert _relerr(out, ref) < 6e-3
 
 
+@pytest.mark.parametrize("block_n", [128, 256, 0])
+def test_gemm_ragged_groups_and_tma_residual(F, block_n):
+    """Groups whose width is a multiple of 64 but not of the tile (llama_1b: 5504): the last tile of a group is
+    ragged.  Also exercises the residual fetched by TMA into the output slab."""
+    torch.manual_seed(3)
+    M, K, G, Ng, r = 300, 192, 2, 320, 128
+    x, W = _rand(M, K), _rand(G * Ng, K, scale=0.05)
+    u, B = _rand(M, G * r), _rand(G * Ng, r, scale=0.05)
+    res = _rand(M, G * Ng)
+    out = torch.full((M, G * Ng), 7.0, device="cuda", dtype=BF)
+    F.gemm(x, W, out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=res, block_n=block_n)
+    want = x.float() @ W.float().t() + res.float()
+    for g in range(G):
+        want[:, g * Ng:(g + 1) * Ng] += u[:, g * r:(g + 1) * r].float() @ B[g * Ng:(g + 1) * Ng].float().t()
+    assert _relerr(out, want) < 5e-3
+    # plain residual GEMM with ragged M / N edges
+    M, N, K = 1000, 520, 200
+    a, b, res = _rand(M, K), _rand(N, K, scale=0.05), _rand(M, N)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    F.gemm(a, b, out, residual=res, block_n=block_n)
+    assert _relerr(out, a.float() @ b.float().t() + res.float()) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [
+    (512, 512, 256, False, False), (1000, 520, 200, False, False), (768, 1024, 384, False, True), (640, 768, 320, True, True),
+    (384, 256, 192, True, False), (12288, 2304, 768, False, False),
+])
+def test_gemm_cta_pair(F, M, N, K, a_mn, b_mn):
+    """tcgen05 cta_group::2: one M=256 instruction per CTA pair, each CTA stages half of the B tile."""
+    torch.manual_seed(M + N)
+    a = _rand(K, M) if a_mn else _rand(M, K)
+    b = _rand(K, N, scale=0.05) if b_mn else _rand(N, K, scale=0.05)
+    out = torch.empty(M, (N + 7) // 8 * 8, device="cuda", dtype=BF)[:, :N]
+    F.gemm(a, b, out, M=M, N=N, K1=K, a1_mn=a_mn, b1_mn=b_mn, block_n=256, pair=1)
+    af = a.float().t() if a_mn else a.float()
+    bf = b.float() if b_mn else b.float().t()
+    assert _relerr(out, af @ bf) < 5e-3
+
+
+def test_gemm_cta_pair_fused_lora_residual_splitk(F):
+    torch.manual_seed(11)
+    M, K, G, Ng, r = 700, 256, 2, 512, 128
+    x, W = _rand(M, K), _rand(G * Ng, K, scale=0.05)
+    u, B = _rand(M, G * r), _rand(G * Ng, r, scale=0.05)
+    res = _rand(M, G * Ng)
+    out = torch.empty(M, G * Ng, device="cuda", dtype=BF)
+    F.gemm(x, W, out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=res, block_n=256, pair=1)
+    want = x.float() @ W.float().t() + res.float()
+    for g in range(G):
+        want[:, g * Ng:(g + 1) * Ng] += u[:, g * r:(g + 1) * r].float() @ B[g * Ng:(g + 1) * Ng].float().t()
+    assert _relerr(out, want) < 5e-3
+    # weight-gradient shape: fp32 accumulate with split-K over the tokens
+    dy, xx = _rand(4096, 512), _rand(4096, 256)
+    dw = torch.ones(512, 256, device="cuda", dtype=torch.float32)
+    F.gemm(dy, xx, dw, M=512, N=256, K1=4096, a1_mn=True, b1_mn=True, accumulate=True, split_k=8, block_n=256, pair=1)
+    assert _relerr(dw, 1.0 + dy.float().t() @ xx.float()) < 5e-3
+
+
 def test_gemm_grouped_a1_window(F):
     """u_g = xd_g A_gᵀ for G groups at once (per-group K window of A1)."""
     torch.manual_seed(3)
@@ -260,6 +318,12 @@ def test_swiglu(C):
     dgu = torch.empty_like(gu)
     C.swiglu_bwd(dh, gu, dgu)
     assert _relerr(dgu[:, :Fd], g.grad) < 6e-3 and _relerr(dgu[:, Fd:], u.grad) < 6e-3
+    # fused dropout-expanded copy == dropout_expand(h) bit for bit
+    seed = torch.tensor([777], dtype=torch.int32, device="cuda")
+    h2, hd, hd_ref = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+    C.swiglu_fwd(gu, h2, hd, seed, 5, 0.1)
+    C.dropout_expand(h, hd_ref, seed, [5], 0.1)
+    assert torch.equal(h2, h) and torch.equal(hd, hd_ref)
 
 
 def test_embedding(C):
