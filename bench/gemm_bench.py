@@ -70,19 +70,29 @@ def main():
         rec = {"shape": name, "M": Mx, "N": N, "K": K, "cublas_us": t_cublas * 1e6, "cublas_tflops": flops / t_cublas / 1e12}
         for bn in (128, 256):
             try:
-                t = timeit(lambda: F.gemm(x, W, out, block_n=bn), flush)
+                t = timeit(lambda: F.gemm(x, W, out, block_n=bn, pair=0), flush)
                 rec[f"ours_bn{bn}_us"] = t * 1e6
                 rec[f"ours_bn{bn}_tflops"] = flops / t / 1e12
                 rec[f"ours_bn{bn}_frac_of_measured_peak"] = flops / t / 1e12 / peak
             except Exception as e:  # keep benchmarking the other variants
                 rec[f"ours_bn{bn}_error"] = str(e)[:200]
+        try:
+            t = timeit(lambda: F.gemm(x, W, out, block_n=256, pair=1), flush)
+            rec["ours_pair_us"] = t * 1e6
+            rec["ours_pair_tflops"] = flops / t / 1e12
+            rec["ours_pair_frac_of_measured_peak"] = flops / t / 1e12 / peak
+        except Exception as e:
+            rec["ours_pair_error"] = str(e)[:200]
         if name != "square_8k":
             Ng = N // G
             bn = 256 if Ng % 256 == 0 else 128
             fl2 = flops + 2.0 * Mx * N * r
-            t = timeit(lambda: F.gemm(x, W, out, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, block_n=bn), flush)
+            t = timeit(lambda: F.gemm(x, W, out, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, block_n=bn, pair=0), flush)
             rec["ours_fused_lora_us"] = t * 1e6
             rec["ours_fused_lora_tflops"] = fl2 / t / 1e12
+            t = timeit(lambda: F.gemm(x, W, out, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, block_n=256, pair=1), flush)
+            rec["ours_fused_lora_pair_us"] = t * 1e6
+            rec["ours_fused_lora_pair_tflops"] = fl2 / t / 1e12
             # what the reference does for the same math: F.linear + 2 small GEMMs + mul + add (no dropout here)
             def ref_path():
                 y = torch.matmul(x, W.t())
@@ -94,9 +104,12 @@ def main():
             # backward dx (B operand read MN-major from W[N,K])
             dy = torch.randn(Mx, N, device=dev).to(BF)
             dx = torch.empty(Mx, K, device=dev, dtype=BF)
-            t = timeit(lambda: F.gemm(dy, W, dx, M=Mx, N=K, K1=N, b1_mn=True), flush)
+            t = timeit(lambda: F.gemm(dy, W, dx, M=Mx, N=K, K1=N, b1_mn=True, pair=0), flush)
             rec["ours_dx_mnB_us"] = t * 1e6
             rec["ours_dx_mnB_tflops"] = flops / t / 1e12
+            t = timeit(lambda: F.gemm(dy, W, dx, M=Mx, N=K, K1=N, b1_mn=True, block_n=256, pair=1), flush)
+            rec["ours_dx_mnB_pair_us"] = t * 1e6
+            rec["ours_dx_mnB_pair_tflops"] = flops / t / 1e12
             t = timeit(lambda: torch.matmul(dy, W, out=dx), flush)
             rec["cublas_dx_us"] = t * 1e6
             # LoRA weight grad: dB[N, r] = dyᵀ u (split-K over tokens)

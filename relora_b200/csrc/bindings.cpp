@@ -102,7 +102,7 @@ void rmsnorm_fwd(const Tensor& x, const Tensor& w, Tensor& y, Tensor& rstd, doub
     for (int i = 0; i < G; ++i) k[i] = (uint32_t)keys[i];
     xdp = xd->data_ptr();
   }
-  const uint32_t thr = (uint32_t)llround(p * 16777216.0);
+  const uint32_t thr = (uint32_t)llround(p * 65536.0);
   rb::rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), M, H, (float)eps, xdp, G, u32ptr(seed), k, thr,
                   (float)(1.0 / (1.0 - p)), cur_stream());
 }
@@ -139,7 +139,7 @@ void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vec
   uint32_t k[4] = {0, 0, 0, 0};
   for (int i = 0; i < G && i < 4; ++i) k[i] = (uint32_t)keys[i];
   c10::cuda::CUDAGuard guard(x.device());
-  rb::dropout_expand(x.data_ptr(), xd.data_ptr(), M, H, G, u32ptr(seed), k, (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)),
+  rb::dropout_expand(x.data_ptr(), xd.data_ptr(), M, H, G, u32ptr(seed), k, (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)),
                      cur_stream());
 }
 
@@ -163,29 +163,39 @@ void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, co
   if (base.has_value()) { chk_bf16(*base, "base"); TORCH_CHECK(base->is_contiguous() && base->numel() == out.numel()); bp = base->data_ptr(); }
   c10::cuda::CUDAGuard guard(out.device());
   rb::dropout_combine(bp, parts.data_ptr(), part_stride, ld_parts, out.data_ptr(), M, H, G, u32ptr(seed), k,
-                      (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
+                      (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 
 // out[M,N] = dy[M,Kb]·W[Kb,N] + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)     (fused input gradient of a stacked LoRA group)
-void lora_dx(const Tensor& dy, const Tensor& w, const Tensor& du, const Tensor& a, Tensor& out, const OptTensor& seed,
-             std::vector<int64_t> keys, double p) {
-  chk_bf16(dy, "dy"); chk_bf16(w, "w"); chk_bf16(du, "du"); chk_bf16(a, "a"); chk_bf16(out, "out");
-  chk_2d_rowmajor(dy, "dy"); chk_2d_rowmajor(w, "w"); chk_2d_rowmajor(du, "du"); chk_2d_rowmajor(a, "a"); chk_2d_rowmajor(out, "out");
+void lora_dx(const OptTensor& dy, const OptTensor& w, const Tensor& du, const Tensor& a, Tensor& out, const OptTensor& seed,
+             std::vector<int64_t> keys, double p, const OptTensor& base) {
+  chk_bf16(du, "du"); chk_bf16(a, "a"); chk_bf16(out, "out");
+  chk_2d_rowmajor(du, "du"); chk_2d_rowmajor(a, "a"); chk_2d_rowmajor(out, "out");
   const int G = (int)keys.size();
   TORCH_CHECK(G >= 1 && G <= 3, "lora_dx: 1..3 groups");
   rb::LoraDxDesc d;
-  d.M = (int)dy.size(0); d.Kb = (int)dy.size(1); d.N = (int)w.size(1); d.groups = G;
-  TORCH_CHECK(w.size(0) == d.Kb, "w must be [Kb, N]");
-  TORCH_CHECK(du.size(0) == d.M && du.size(1) % G == 0, "du must be [M, G*r]");
+  d.M = (int)du.size(0); d.N = (int)a.size(1); d.groups = G;
+  TORCH_CHECK(du.size(1) % G == 0, "du must be [M, G*r]");
   d.r = (int)(du.size(1) / G);
-  TORCH_CHECK(a.size(0) == du.size(1) && a.size(1) == d.N, "a must be [G*r, N]");
+  TORCH_CHECK(a.size(0) == du.size(1), "a must be [G*r, N]");
   TORCH_CHECK(out.size(0) == d.M && out.size(1) == d.N, "out must be [M, N]");
-  d.dy = dy.data_ptr(); d.ld_dy = dy.stride(0);
-  d.w = w.data_ptr(); d.ld_w = w.stride(0);
+  if (base.has_value()) {
+    // two-kernel form: base = dy·W from the plain GEMM, this launch adds the masked low-rank terms
+    chk_bf16(*base, "base"); chk_2d_rowmajor(*base, "base");
+    TORCH_CHECK(base->size(0) == d.M && base->size(1) == d.N, "base must be [M, N]");
+    d.base = base->data_ptr(); d.ld_base = base->stride(0); d.Kb = 0;
+  } else {
+    TORCH_CHECK(dy.has_value() && w.has_value(), "lora_dx: pass (dy, w) or base");
+    chk_bf16(*dy, "dy"); chk_bf16(*w, "w"); chk_2d_rowmajor(*dy, "dy"); chk_2d_rowmajor(*w, "w");
+    d.Kb = (int)dy->size(1);
+    TORCH_CHECK(dy->size(0) == d.M && w->size(0) == d.Kb && w->size(1) == d.N, "dy must be [M, Kb], w [Kb, N]");
+    d.dy = dy->data_ptr(); d.ld_dy = dy->stride(0);
+    d.w = w->data_ptr(); d.ld_w = w->stride(0);
+  }
   d.du = du.data_ptr(); d.ld_du = du.stride(0);
   d.a = a.data_ptr(); d.ld_a = a.stride(0);
   d.out = out.data_ptr(); d.ldc = out.stride(0);
-  d.drop_threshold24 = (uint32_t)llround(p * 16777216.0);
+  d.drop_threshold16 = (uint32_t)llround(p * 65536.0);
   d.inv_keep = (float)(1.0 / (1.0 - p));
   d.seed_ptr = u32ptr(seed);
   for (int i = 0; i < G; ++i) d.seed_key[i] = (uint32_t)keys[i];
@@ -230,7 +240,7 @@ void swiglu_fwd(const Tensor& gu, Tensor& h, const OptTensor& hd, const OptTenso
   }
   c10::cuda::CUDAGuard guard(gu.device());
   rb::swiglu_fwd(gu.data_ptr(), gu.stride(0), h.data_ptr(), h.stride(0), (int)h.size(0), F, hdp, ldhd, u32ptr(seed), (uint32_t)key,
-                 (uint32_t)llround(p * 16777216.0), (float)(1.0 / (1.0 - p)), cur_stream());
+                 (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
   chk_bf16(dh, "dh"); chk_bf16(gu, "gu"); chk_bf16(dgu, "dgu");
@@ -385,12 +395,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "relora_b200 sm_100a kernels";
   m.def("gemm", &gemm, "tcgen05 GEMM with fused LoRA K-extension");
   m.def("gemm_clear_descriptor_cache", &rb::gemm_clear_descriptor_cache);
+  m.def("gemm_pair_clusters", &rb::gemm_pair_clusters);
+  m.def("gemm_set_trace", [](const OptTensor& t) {
+    if (!t.has_value()) { rb::gemm_set_trace(nullptr); return; }
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 12 * 512, "trace buffer: int64 CUDA tensor of >= 6144 elements");
+    rb::gemm_set_trace(t->data_ptr());
+  });
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
   m.def("dropout_expand", &dropout_expand);
   m.def("dropout_combine", &dropout_combine);
-  m.def("lora_dx", &lora_dx);
+  m.def("lora_dx", &lora_dx, py::arg("dy"), py::arg("w"), py::arg("du"), py::arg("a"), py::arg("out"), py::arg("seed"), py::arg("keys"),
+        py::arg("p"), py::arg("base") = py::none());
   m.def("rope_inplace", &rope_inplace);
   m.def("rope_pack_bwd", &rope_pack_bwd);
   m.def("swiglu_fwd", &swiglu_fwd, py::arg("gu"), py::arg("h"), py::arg("hd") = py::none(), py::arg("seed") = py::none(),

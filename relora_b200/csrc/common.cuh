@@ -60,6 +60,17 @@ __host__ __device__ __forceinline__ uint32_t hash_rc(uint32_t seed, uint32_t row
 __host__ __device__ __forceinline__ bool keep_bit(uint32_t seed, uint32_t row, uint32_t col, uint32_t threshold24) {
   return (hash_rc(seed, row, col) >> 8) >= threshold24;
 }
+// Dropout keep mask: one hash per column PAIR, 16-bit threshold (halves the integer work of every dropout consumer;
+// it was the bound of the fused LoRA-backward epilogue and of the RMSNorm forward with three expanded copies):
+//   h = lowbias32(row*C1 ^ (col>>1)*C2 ^ seed);  keep(row, col) = ((col & 1) ? h >> 16 : h & 0xFFFF) >= round(p * 2^16)
+// Same definition in ops/reference.py:dropout_keep_mask.
+__host__ __device__ __forceinline__ uint32_t drop_hash2(uint32_t seed, uint32_t row, uint32_t col) {
+  return lowbias32((row * 0x9E3779B1u) ^ ((col >> 1) * 0x85EBCA77u) ^ seed);
+}
+__host__ __device__ __forceinline__ bool keep_drop(uint32_t seed, uint32_t row, uint32_t col, uint32_t thr16) {
+  const uint32_t h = drop_hash2(seed, row, col);
+  return ((col & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thr16;
+}
 __host__ __device__ __forceinline__ uint32_t mix_seed(uint32_t base, uint32_t key) {
   uint32_t x = base ^ key;
   x = (x ^ (x >> 16)) * 0x7FEB352Du;

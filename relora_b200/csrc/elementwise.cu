@@ -12,7 +12,7 @@ namespace rb {
 template <int VPT>  // bf16x8 vectors per thread
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                           float* __restrict__ rstd_out, int M, int H, float eps, bf16* __restrict__ xd,
-                                                          int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr24,
+                                                          int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16,
                                                           float inv_keep) {
   __shared__ float scratch[32];
   const int row = blockIdx.x;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict
       for (int g = 0; g < G; ++g) {
         float d[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24) ? o[j] * inv_keep : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = keep_drop(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr16) ? o[j] * inv_keep : 0.f;
         reinterpret_cast<bf16x8*>(xd + ((long long)row * G + g) * H)[c] = pack8(d);
       }
     }
@@ -60,18 +60,18 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict
 }
 
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s) {
+                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, cudaStream_t s) {
   if (H % 8 != 0 || H > 8 * 256 * 4) throw std::runtime_error("rmsnorm: H must be a multiple of 8 and <= 8192");
   if (G > 4) throw std::runtime_error("rmsnorm: at most 4 dropout groups");
   uint4 k = make_uint4(0, 0, 0, 0);
   if (G > 0) k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
-  if (rmsnorm_fwd_warp(x, w, y, rstd, M, H, eps, xd, G, seed_ptr, k, thr24, inv_keep, s)) return;
+  if (rmsnorm_fwd_warp(x, w, y, rstd, M, H, eps, xd, G, seed_ptr, k, thr16, inv_keep, s)) return;
   const int nvec = H / 8;
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)w;
   bf16 *yp = (bf16*)y, *xdp = (bf16*)xd;
-  if (nvec <= 256) rmsnorm_fwd_kernel<1><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr24, inv_keep);
-  else if (nvec <= 512) rmsnorm_fwd_kernel<2><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr24, inv_keep);
-  else rmsnorm_fwd_kernel<4><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr24, inv_keep);
+  if (nvec <= 256) rmsnorm_fwd_kernel<1><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr16, inv_keep);
+  else if (nvec <= 512) rmsnorm_fwd_kernel<2><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr16, inv_keep);
+  else rmsnorm_fwd_kernel<4><<<M, 256, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, k, thr16, inv_keep);
   RB_CHECK_LAUNCH("rmsnorm_fwd");
 }
 
@@ -158,7 +158,7 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
 
 // ============================================================================================ LoRA dropout
 __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restrict__ x, bf16* __restrict__ xd, long long n_vec, int H,
-                                                             int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr24,
+                                                             int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16,
                                                              float inv_keep) {
   const uint32_t base = seed_ptr ? *seed_ptr : 0u;
   const uint32_t seeds[4] = {mix_seed(base, keys.x), mix_seed(base, keys.y), mix_seed(base, keys.z), mix_seed(base, keys.w)};
@@ -181,27 +181,27 @@ __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restr
       for (int g = 0; g < G; ++g) {
         float d[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24) ? f[j] * inv_keep : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = keep_drop(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr16) ? f[j] * inv_keep : 0.f;
         reinterpret_cast<bf16x8*>(xd + (row * G + g) * H)[c] = pack8(d);
       }
     }
   }
 }
 
-void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24,
+void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16,
                     float inv_keep, cudaStream_t s) {
   if (H % 8 != 0 || G < 1 || G > 4) throw std::runtime_error("dropout_expand: bad shape");
   uint4 k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
   const long long n_vec = (long long)M * H / 8;
   const int grid = (int)std::min<long long>((n_vec + 255) / 256, (long long)num_sms() * 8);
-  dropout_expand_kernel<<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)xd, n_vec, H, G, seed_ptr, k, thr24, inv_keep);
+  dropout_expand_kernel<<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)xd, n_vec, H, G, seed_ptr, k, thr16, inv_keep);
   RB_CHECK_LAUNCH("dropout_expand");
 }
 
 __global__ void __launch_bounds__(256) dropout_combine_kernel(const bf16* __restrict__ basep, const bf16* __restrict__ parts,
                                                               long long part_stride, long long ld_parts, bf16* __restrict__ out,
                                                               long long n_vec, int H, int G,
-                                                              const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr24,
+                                                              const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16,
                                                               float inv_keep) {
   const uint32_t base = seed_ptr ? *seed_ptr : 0u;
   const uint32_t seeds[4] = {mix_seed(base, keys.x), mix_seed(base, keys.y), mix_seed(base, keys.z), mix_seed(base, keys.w)};
@@ -220,20 +220,20 @@ __global__ void __launch_bounds__(256) dropout_combine_kernel(const bf16* __rest
       unpack8(*reinterpret_cast<const bf16x8*>(parts + g * part_stride + row * ld_parts + c * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (keep_bit(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr24)) acc[j] += f[j] * inv_keep;
+        if (keep_drop(seeds[g], (uint32_t)row, (uint32_t)(c * 8 + j), thr16)) acc[j] += f[j] * inv_keep;
     }
     reinterpret_cast<bf16x8*>(out)[i] = pack8(acc);
   }
 }
 
 void dropout_combine(const void* base, const void* parts, long long part_stride, long long ld_parts, void* out, int M, int H, int G,
-                     const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr24, float inv_keep, cudaStream_t s) {
+                     const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, cudaStream_t s) {
   if (H % 8 != 0 || G < 1 || G > 4) throw std::runtime_error("dropout_combine: bad shape");
   uint4 k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
   const long long n_vec = (long long)M * H / 8;
   const int grid = (int)std::min<long long>((n_vec + 255) / 256, (long long)num_sms() * 8);
   dropout_combine_kernel<<<grid, 256, 0, s>>>((const bf16*)base, (const bf16*)parts, part_stride, ld_parts, (bf16*)out, n_vec, H, G, seed_ptr, k,
-                                              thr24, inv_keep);
+                                              thr16, inv_keep);
   RB_CHECK_LAUNCH("dropout_combine");
 }
 
@@ -279,7 +279,7 @@ void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd
 // down_proj consumes) so that h is not re-read by a separate dropout kernel.  Two vectors in flight per thread.
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ldgu, bf16* __restrict__ h, long long ldh,
                                                          int M, int F, bf16* __restrict__ hd, long long ldhd,
-                                                         const uint32_t* __restrict__ seed_ptr, uint32_t key, uint32_t thr24, float inv_keep) {
+                                                         const uint32_t* __restrict__ seed_ptr, uint32_t key, uint32_t thr16, float inv_keep) {
   const int fv = F / 8;
   const long long total = (long long)M * fv;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
         float ob[8], d[8];
         unpack8(packed, ob);  // the mask multiplies the rounded activation, exactly like dropout_expand(h)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = keep_bit(seed, (uint32_t)row, (uint32_t)(c + j), thr24) ? ob[j] * inv_keep : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = keep_drop(seed, (uint32_t)row, (uint32_t)(c + j), thr16) ? ob[j] * inv_keep : 0.f;
         *reinterpret_cast<bf16x8*>(hd + row * ldhd + c) = pack8(d);
       }
     }
@@ -338,11 +338,11 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
   }
 }
 void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, void* hd, long long ldhd,
-                const uint32_t* seed_ptr, uint32_t key, uint32_t thr24, float inv_keep, cudaStream_t s) {
+                const uint32_t* seed_ptr, uint32_t key, uint32_t thr16, float inv_keep, cudaStream_t s) {
   if (F % 8 || ldgu % 8 || ldh % 8 || (hd != nullptr && ldhd % 8)) throw std::runtime_error("swiglu: F and leading dims must be multiples of 8");
   const long long total = (long long)M * (F / 8);
   const int grid = (int)std::min<long long>((total + 511) / 512, (long long)num_sms() * 8);
-  swiglu_fwd_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>((const bf16*)gu, ldgu, (bf16*)h, ldh, M, F, (bf16*)hd, ldhd, seed_ptr, key, thr24, inv_keep);
+  swiglu_fwd_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>((const bf16*)gu, ldgu, (bf16*)h, ldh, M, F, (bf16*)hd, ldhd, seed_ptr, key, thr16, inv_keep);
   RB_CHECK_LAUNCH("swiglu_fwd");
 }
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,

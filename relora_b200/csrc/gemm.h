@@ -65,7 +65,11 @@ struct LoraDxDesc {
   void* out = nullptr;
   long long ldc = 0;
   int M = 0, N = 0, Kb = 0, r = 0, groups = 1;
-  uint32_t drop_threshold24 = 0;  // 0 = keep everything (no dropout)
+  // Kb == 0: `base` [M, N] bf16 already holds dy·W (computed by the 256-wide / CTA-pair GEMM, the better choice for long
+  // reductions); this kernel then only adds the masked low-rank terms
+  const void* base = nullptr;
+  long long ld_base = 0;
+  uint32_t drop_threshold16 = 0;  // round(p * 65536); 0 = keep everything (no dropout)
   float inv_keep = 1.0f;
   const uint32_t* seed_ptr = nullptr;
   uint32_t seed_key[3] = {0, 0, 0};
@@ -74,5 +78,12 @@ void lora_dx(const LoraDxDesc& d, cudaStream_t stream);
 
 // Drop cached TMA descriptors (call when buffers are freed / reallocated).
 void gemm_clear_descriptor_cache();
+
+// Co-resident CTA pairs the hardware reports for the cta_group::2 GEMM (0 until the first pair launch).
+int gemm_pair_clusters();
+
+// Diagnostics: CTA 0 of every following GEMM launch writes clock64 stamps of its pipeline events into `buf`
+// (6 x 512 int64: producer issue / MMA full / MMA acc-free / MMA tile commit / epilogue start / epilogue end); nullptr = off.
+void gemm_set_trace(void* buf);
 
 }  // namespace rb

@@ -14,6 +14,7 @@
 //   warps 4-7 epilogue         (128 threads == 128 TMEM lanes == 128 rows of the tile)
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -24,7 +25,13 @@
 
 namespace rb {
 
+#define RB_TR(slot) do { if (p.trace != nullptr && blockIdx.x == 0 && issuer && sl == 0 && tr_e < 512) p.trace[(slot) * 512 + tr_e] = clock64(); } while (0)
+
 long long g_launch_count = 0;
+void* g_trace_ptr = nullptr;  // diagnostics: device buffer of 6 x 512 int64 (gemm_set_trace)
+void gemm_set_trace(void* p) { g_trace_ptr = p; }
+int g_pair_clusters = 0;  // cudaOccupancyMaxActiveClusters of the CTA-pair GEMM (diagnostics)
+int gemm_pair_clusters() { return g_pair_clusters; }
 
 using namespace sm100;
 
@@ -49,6 +56,8 @@ struct KernelArgs {
   int num_m_tiles, num_n_tiles;
   int tiles_per_group;  // N-tiles per output-column group (the last one of a group may be ragged)
   int use_tma_store;  // bf16 output written through swizzled smem slabs + TMA store
+  long long* trace;   // diagnostics: clock64 stamps of CTA 0 (see bench/gemm_trace.py), normally null
+  int debug;          // RB_GEMM_DEBUG (diagnostics only): 1 = skip TMA store, 2 = skip TMEM loads, 4 = skip slab writes
   int res_tma;        // ... and the residual is fetched into the same slab by TMA (coalesced) instead of per-row loads
   int split_k;  // >1: each output tile is computed by split_k CTAs over disjoint K ranges, combined with fp32 atomics
 };
@@ -59,11 +68,12 @@ struct SmemLayout {
   static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // CTA pair: each CTA stages half of the B tile
   static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kStageBytes <= 32768) ? 5 : 3;
+  static constexpr int kStages = (kStageBytes <= 32768) ? 5 : 4;  // load->full latency is 1000-2200 cycles, one k-block is 512
   static constexpr int kTileBytes = kStages * kStageBytes;
   static constexpr int kBarrierBytes = 1024;                          // barriers + tmem slot (keeps the slabs 1024-aligned)
   static constexpr int kSlabBytes = BLOCK_M * 128;                    // one 128 x 64 bf16 output slab (128B swizzle)
-  static constexpr int kTotal = kTileBytes + kBarrierBytes + 2 * kSlabBytes + 1024;  // +1024 for manual alignment
+  static constexpr int kSlabs = (kStageBytes <= 32768) ? 4 : 2;       // rotating output slabs; the rest of smem feeds the MMA
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + kSlabs * kSlabBytes + 1024;  // +1024 for manual alignment
 };
 
 // Issue the TMA loads of one operand tile (BLOCK_MN x BLOCK_K) into `dst`; `bar` is the 32-bit shared address of the
@@ -130,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_bar = tmem_empty_bar + 2;  // residual slab landed (TMA load into the output slab, see epilogue)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + L::kSlabs);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -153,8 +163,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], PAIR ? 256 : 128);  // pair: the epilogues of both CTAs release the leader's barrier
-      mbar_init(&res_bar[a], 1);
     }
+    for (int a = 0; a < L::kSlabs; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -184,6 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tr_p = 0;
       const uint32_t full_addr0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
       const int b_half = PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0;  // this CTA's share of the B tile
       for (int work = work0; work < num_work; work += work_step) {
@@ -202,6 +213,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
+          if (p.trace != nullptr && blockIdx.x == 0 && tr_p < 512) p.trace[0 * 512 + tr_p++] = clock64();
           const uint32_t fb = full_addr0 + stage * 8;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * L::kStageBytes);  // both CTAs' bytes land here
           if (kb < kb1) {
@@ -236,15 +248,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int tr_m = 0, tr_t = 0;
       for (int work = work0; work < num_work; work += work_step) {
         const int split = work % p.split_k;
         const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (p.trace != nullptr && blockIdx.x == 0 && tr_t < 512) p.trace[2 * 512 + tr_t] = clock64();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (p.trace != nullptr && blockIdx.x == 0 && tr_m < 512) p.trace[1 * 512 + tr_m++] = clock64();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
           if (kb < kb1) {
@@ -263,6 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           }
         }
         commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue(s)
+        if (p.trace != nullptr && blockIdx.x == 0 && tr_t < 512) p.trace[3 * 512 + tr_t++] = clock64();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -282,7 +298,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     uint32_t acc_phase = 0;
     const bool res_vec = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const bool out_vec = (p.ldc % (p.out_f32 ? 4 : 8) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool lean = p.bias == nullptr && (p.residual == nullptr || p.res_tma);  // epilogue is alpha (+ TMA residual) only
     int slab_counter = 0;
+    int tr_e = 0;
     // residual slabs travel by TMA into the (swizzled) output slab one slab ahead of their use; each thread then
     // reads back exactly the 16-byte chunks it is about to overwrite
     auto slab_coords = [&](int work_i, int sl_i, int& c_col, int& c_row) {
@@ -308,14 +326,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
       const bool empty_split = split * kb_per_split >= num_kb;  // nothing was accumulated for this work item
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.trace != nullptr && blockIdx.x == 0 && issuer && tr_e < 512) p.trace[4 * 512 + tr_e] = clock64();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int sl = 0; sl < BLOCK_N / 64; ++sl) {
         uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64), r0);
-        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64 + 32), r1);
-        tmem_ld_wait();
+        if (!(p.debug & 2)) {
+          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64), r0);
+          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, acc * BLOCK_N + sl * 64 + 32), r1);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0x3f800000u;
+        }
+        RB_TR(6);  // TMEM loads returned
         if (sl == BLOCK_N / 64 - 1) {  // accumulator fully read: hand it back to the MMA warp early
           tc_fence_before();
           if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_addr0 + acc * 8);
@@ -324,54 +349,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         const int col0 = n0 + sl * 64;
         if (p.use_tma_store) {
           // ---- (a) bf16 via swizzled smem + TMA store
-          uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
+          // kSlabs buffers rotate; the issuer's wait_read<kSlabs-2> after every commit (two iterations ago, ordered by
+          // the barrier of the previous iteration) guarantees the store that last used this buffer has read it
+          const int sb_i = slab_counter % L::kSlabs;
+          uint8_t* slab = stage_base + sb_i * L::kSlabBytes;
           const uint32_t rloc = quad * 32 + lane;
           uint8_t* rowp = slab + rloc * 128;
-          if (p.res_tma) {
-            mbar_wait(&res_bar[slab_counter & 1], (slab_counter >> 1) & 1);  // residual slab landed (slab was free before the load)
-          } else {
-            if (issuer) tma_store_wait_read<1>();  // the store that used this slab two slabs ago has drained
-            named_bar_sync(1, 128);
-          }
+          if (p.res_tma) mbar_wait(&res_bar[sb_i], (slab_counter / L::kSlabs) & 1);  // residual slab landed
           uint4 packed[8];
+          // Three separately compiled variants behind uniform branches.  A single loop with per-element `if (bias)` /
+          // `if (residual)` tests is if-converted by the compiler into ~1600 predicated instructions that are issued
+          // (and cost ~1800 cycles per slab) even when every predicate is false.
+          if (!lean) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float f[8];
+            for (int q = 0; q < 8; ++q) {
+              float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-              f[i] = __uint_as_float(raw) * p.alpha;
-            }
-            add_bias8(p.bias, col0 + q * 8, n_lim, f);
-            if (p.res_tma) {
-              float a[8];
-              unpack8(*reinterpret_cast<const uint4*>(rowp + ((q ^ (rloc & 7)) << 4)), a);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] += a[i];
-            } else if (p.residual != nullptr && row_ok) {
-              const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
-              if (res_vec && col0 + q * 8 + 8 <= n_lim) {
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+                f[i] = __uint_as_float(raw) * p.alpha;
+              }
+              add_bias8(p.bias, col0 + q * 8, n_lim, f);
+              if (p.res_tma) {
                 float a[8];
-                unpack8(*reinterpret_cast<const uint4*>(rp), a);
+                unpack8(*reinterpret_cast<const uint4*>(rowp + ((q ^ (rloc & 7)) << 4)), a);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += a[i];
-              } else {
+              } else if (p.residual != nullptr && row_ok) {
+                const bf16* rp = p.residual + (long long)row * p.ldr + col0 + q * 8;
+                if (res_vec && col0 + q * 8 + 8 <= n_lim) {
+                  float a[8];
+                  unpack8(*reinterpret_cast<const uint4*>(rp), a);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (col0 + q * 8 + i < n_lim) f[i] += __bfloat162float(rp[i]);
+                  for (int i = 0; i < 8; ++i) f[i] += a[i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (col0 + q * 8 + i < n_lim) f[i] += __bfloat162float(rp[i]);
+                }
               }
+              packed[q] = pack8(f);
             }
-            packed[q] = pack8(f);
-          }
+          } else if (p.res_tma) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
+            for (int q = 0; q < 8; ++q) {
+              float f[8], a[8];
+              unpack8(*reinterpret_cast<const uint4*>(rowp + ((q ^ (rloc & 7)) << 4)), a);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+                f[i] = fmaf(__uint_as_float(raw), p.alpha, a[i]);
+              }
+              packed[q] = pack8(f);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+                f[i] = __uint_as_float(raw) * p.alpha;
+              }
+              packed[q] = pack8(f);
+            }
+          }
+          RB_TR(7);  // math done
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
+          } else if (packed[0].x == 0x12345u) {
+            *reinterpret_cast<uint4*>(rowp) = packed[7];
+          }
+          RB_TR(8);  // slab written
           fence_proxy_async_smem();
+          RB_TR(9);  // proxy fence
           named_bar_sync(1, 128);
-          if (issuer && !empty_split && col0 < n_lim) {
+          RB_TR(10);  // barrier
+          if (issuer && !empty_split && col0 < n_lim && !(p.debug & 1)) {
             tma_store_2d(&map_out, slab, col0, m0);
             tma_store_commit();
           }
-          if (p.res_tma && issuer) {  // prefetch the next slab's residual into the other buffer
+          if (issuer) tma_store_wait_read<L::kSlabs - 2>();  // frees the buffer of the NEXT slab (see above)
+          RB_TR(11);  // store issued + wait_read
+          if (p.res_tma && issuer) {  // prefetch the next slab's residual into the next buffer
             int nwork = work, nsl = sl + 1;
             if (nsl == BLOCK_N / 64) {
               nsl = 0;
@@ -380,8 +441,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
             if (nwork < num_work) {
               int c_col, c_row;
               slab_coords(nwork, nsl, c_col, c_row);
-              tma_store_wait_read<1>();  // every store but the one just committed has read its slab: the other buffer is free
-              const int nb = (slab_counter + 1) & 1;
+              const int nb = (slab_counter + 1) % L::kSlabs;
               mbar_arrive_expect_tx(&res_bar[nb], L::kSlabBytes);
               tma_load_2d(&map_res, &res_bar[nb], stage_base + nb * L::kSlabBytes, c_col, c_row, kEvictNormal);
             }
@@ -389,7 +449,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           ++slab_counter;
         } else if (row_ok && !empty_split && col0 < n_lim) {
           // ---- (b) direct global path
-          if (p.split_k > 1) {
+          if (p.split_k > 1 && out_vec && col0 + 64 <= n_lim) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
+              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
+              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
+              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + q * 4), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+            }
+          } else if (p.split_k > 1) {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -405,6 +475,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (col0 + q * 4 + i < n_lim) atomicAdd(op + q * 4 + i, e[i]);
+              }
+            }
+          } else if (p.out_f32 && out_vec && col0 + 64 <= n_lim) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                float4 o = *reinterpret_cast<const float4*>(op + q * 4);
+                o.x = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]), p.alpha, o.x);
+                o.y = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]), p.alpha, o.y);
+                o.z = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]), p.alpha, o.z);
+                o.w = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]), p.alpha, o.w);
+                *reinterpret_cast<float4*>(op + q * 4) = o;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                float4 o;
+                o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
+                o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
+                o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
+                o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+                *reinterpret_cast<float4*>(op + q * 4) = o;
               }
             }
           } else if (p.out_f32) {
@@ -471,6 +564,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           }
         }
       }
+      if (p.trace != nullptr && blockIdx.x == 0 && issuer && tr_e < 512) p.trace[5 * 512 + tr_e++] = clock64();
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -503,8 +597,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 // Reference math: backward of relora.py:319-322 with nn.Dropout on the LoRA input.
 struct LoraDxArgs {
   int M, N, Kb, r;
+  const bf16* base;  // Kb == 0: the frozen-path product was computed by a separate (256-wide / CTA-pair) GEMM
+  long long ld_base;
   int num_m_tiles, num_n_tiles;
-  uint32_t thr24;
+  uint32_t thr16;
   float inv_keep;
   const uint32_t* seed_ptr;
   uint32_t keys[3];
@@ -630,13 +726,13 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
           for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
         }
         umma_commit(&lora_full[ls]);
-        mbar_wait(&base_empty[bs], bs_phase ^ 1);
-        tc_fence_after();
-        {
+        if (kb_base > 0) {
+          mbar_wait(&base_empty[bs], bs_phase ^ 1);
+          tc_fence_after();
           const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
           for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
+          umma_commit(&base_full[bs]);
         }
-        umma_commit(&base_full[bs]);
         if (++ls == kLoraStages) {
           ls = 0;
           ls_phase ^= 1;
@@ -681,10 +777,11 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
           tmem_ld_wait();
           const uint32_t sg = rowmix ^ seeds[g];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint32_t col = (uint32_t)(n0 + ch * 16 + i);
-            const uint32_t hsh = lowbias32(sg ^ (col * 0x85EBCA77u));
-            if ((hsh >> 8) >= p.thr24) cf[i] += __uint_as_float(rr[i]);
+          for (int i = 0; i < 16; i += 2) {  // one hash per column pair (common.cuh:keep_drop)
+            const uint32_t cp = (uint32_t)(n0 + ch * 16 + i) >> 1;
+            const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
+            if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[i]);
+            if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[i + 1]);
           }
         }
 #pragma unroll
@@ -693,35 +790,58 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
       tc_fence_before();
       mbar_arrive(&lora_empty[ls]);
       // ---- phase 2: frozen-path accumulator + combined LoRA term -> bf16 slab -> TMA store
-      mbar_wait(&base_full[bs], bs_phase);
-      tc_fence_after();
+      if (kb_base > 0) {
+        mbar_wait(&base_full[bs], bs_phase);
+        tc_fence_after();
+      }
 #pragma unroll
       for (int sl = 0; sl < BLOCK_N / 64; ++sl) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64), r0);
-        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64 + 32), r1);
-        tmem_ld_wait();
-        if (sl == BLOCK_N / 64 - 1) {
-          tc_fence_before();
-          mbar_arrive(&base_empty[bs]);
-        }
-        uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        uint8_t* slab = stage_base + (slab_counter % L::kSlabs) * L::kSlabBytes;  // freed by wait_read two iterations ago
         uint4 packed[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
-            const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-            const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-            const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
-            f[i] = __uint_as_float(raw0) + c2.x;
-            f[i + 1] = __uint_as_float(raw1) + c2.y;
+        if (kb_base > 0) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64), r0);
+          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64 + 32), r1);
+          tmem_ld_wait();
+          if (sl == BLOCK_N / 64 - 1) {
+            tc_fence_before();
+            mbar_arrive(&base_empty[bs]);
           }
-          packed[q] = pack8(f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
+              const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+              const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+              const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
+              f[i] = __uint_as_float(raw0) + c2.x;
+              f[i + 1] = __uint_as_float(raw1) + c2.y;
+            }
+            packed[q] = pack8(f);
+          }
+        } else {
+          // frozen-path product read back from global memory (this thread's row: 8 x 16 B of one 128-byte line)
+          const bool row_in = (int)row < p.M;
+          const bf16* bp = p.base + (long long)row * p.ld_base + n0 + sl * 64;
+          uint4 bv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            bv[q] = (row_in && n0 + sl * 64 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + q * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+            unpack8(bv[q], f);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
+              const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+              f[i] += c2.x;
+              f[i + 1] += c2.y;
+            }
+            packed[q] = pack8(f);
+          }
         }
         const uint32_t rloc = quad * 32 + lane;
         uint8_t* rowp = slab + rloc * 128;
@@ -732,6 +852,7 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
         if (issuer) {
           tma_store_2d(&map_out, slab, n0 + sl * 64, m0);
           tma_store_commit();
+          tma_store_wait_read<L::kSlabs - 2>();
         }
         ++slab_counter;
       }
@@ -816,8 +937,19 @@ static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // the driver call needs the primary context current on THIS thread; autograd worker threads only bind it lazily.
+    // cudaSetDevice binds it and, unlike cudaFree(0), is legal while a stream is being captured.
+    int dev = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    check(cudaSetDevice(dev), "cudaSetDevice");
+    r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();  // eager runs see fresh activation pointers every step: bound the cache
   g_maps.emplace(key, m);
   return m;
 }
@@ -901,6 +1033,7 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
         n = num_sms() / 2;
       }
       max_clusters = n;
+      g_pair_clusters = n;
     }
     grid = 2 * (work < max_clusters ? work : max_clusters);  // one CTA pair per work item
   }
@@ -909,6 +1042,15 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
                      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0) ? 1 : 0;
   CUtensorMap mout = ma1, mres = ma1;
   if (p.use_tma_store) mout = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("RB_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+    p.trace = reinterpret_cast<long long*>(g_trace_ptr);
+  }
   p.res_tma = (p.use_tma_store && d.residual != nullptr && (d.ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) ? 1 : 0;
   if (p.res_tma) mres = make_map_2d(d.residual, d.N, d.M, d.ldr, 64, BLOCK_M);
   if (PAIR) {
@@ -950,7 +1092,8 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   // CTA pairs (cta_group::2, M = 256 per instruction): each CTA stages only half of the B tile, which cuts the
   // L2 -> shared-memory traffic per FLOP by a third (these GEMMs sit at the ~6.3 KB/clk L2 limit with single CTAs)
   int pair = d.cta_pair;
-  if (pair < 0) pair = (bn == 256 && d.M >= 512 && (d.m_per_group == 0 || d.m_per_group % 256 == 0)) ? 1 : 0;
+  // measured (M 12288, N 2304): equal at K = 768, pairs 3-6 % faster from K = 1536 up, single CTAs faster below
+  if (pair < 0) pair = (bn == 256 && d.M >= 512 && d.K1 + d.K2 >= 1024 && (d.m_per_group == 0 || d.m_per_group % 256 == 0)) ? 1 : 0;
   if (pair && bn != 256) throw std::runtime_error("gemm: CTA pairs need block_n = 256");
   if (bn == 256) {
     if (pair) dispatch_major<256, true>(d, stream);
@@ -965,15 +1108,19 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   using L = SmemLayout<128>;
   LoraDxArgs p;
   p.M = d.M; p.N = d.N; p.Kb = d.Kb; p.r = d.r;
+  p.base = reinterpret_cast<const bf16*>(d.base); p.ld_base = d.ld_base;
   p.num_m_tiles = ceil_div(d.M, BLOCK_M);
   p.num_n_tiles = ceil_div(d.N, 128);
-  p.thr24 = d.drop_threshold24; p.inv_keep = d.inv_keep; p.seed_ptr = d.seed_ptr;
+  p.thr16 = d.drop_threshold16; p.inv_keep = d.inv_keep; p.seed_ptr = d.seed_ptr;
   for (int g = 0; g < 3; ++g) p.keys[g] = d.seed_key[g];
-  CUtensorMap m_dy = make_map_2d(d.dy, d.Kb, d.M, d.ld_dy, BLOCK_K, BLOCK_M);
-  CUtensorMap m_w = make_map_2d(d.w, d.N, d.Kb, d.ld_w, 64, BLOCK_K);
   CUtensorMap m_du = make_map_2d(d.du, (long long)G * d.r, d.M, d.ld_du, BLOCK_K, BLOCK_M);
   CUtensorMap m_a = make_map_2d(d.a, d.N, (long long)G * d.r, d.ld_a, 64, BLOCK_K);
   CUtensorMap m_out = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
+  CUtensorMap m_dy = m_du, m_w = m_a;  // unused when the frozen-path product is supplied (Kb == 0)
+  if (d.Kb > 0) {
+    m_dy = make_map_2d(d.dy, d.Kb, d.M, d.ld_dy, BLOCK_K, BLOCK_M);
+    m_w = make_map_2d(d.w, d.N, d.Kb, d.ld_w, 64, BLOCK_K);
+  }
   auto kern = lora_dx_kernel<G>;
   static bool configured = false;
   if (!configured) {
@@ -991,6 +1138,8 @@ void lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   if (d.M <= 0 || d.N <= 0) return;
   if (d.groups < 1 || d.groups > 3) throw std::runtime_error("lora_dx: 1..3 stacked LoRA groups");
   if (d.r <= 0 || d.r % BLOCK_K != 0) throw std::runtime_error("lora_dx: the LoRA rank must be a multiple of 64");
+  if (d.Kb == 0 && (d.base == nullptr || d.ld_base % 8 != 0 || (reinterpret_cast<uintptr_t>(d.base) & 15) != 0))
+    throw std::runtime_error("lora_dx: Kb == 0 needs a 16-byte aligned base product");
   if (d.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) throw std::runtime_error("lora_dx: output must be 16-byte aligned");
   if (d.groups == 1) launch_lora_dx<1>(d, stream);
   else if (d.groups == 2) launch_lora_dx<2>(d, stream);

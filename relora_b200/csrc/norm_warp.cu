@@ -13,7 +13,7 @@ constexpr int kWarpsPerBlock = 8;
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
     const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, float* __restrict__ rstd_out, int M, int H, float eps,
-    bf16* __restrict__ xd, int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr24, float inv_keep) {
+    bf16* __restrict__ xd, int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16, float inv_keep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * kWarpsPerBlock + warp;
   if (row >= M) return;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
         const uint32_t sd = g == 0 ? s0 : (g == 1 ? s1 : (g == 2 ? s2 : s3));
         float d[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = keep_bit(sd, (uint32_t)row, (uint32_t)(c * 8 + j), thr24) ? o[j] * inv_keep : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = keep_drop(sd, (uint32_t)row, (uint32_t)(c * 8 + j), thr16) ? o[j] * inv_keep : 0.f;
         reinterpret_cast<uint4*>(xd + ((long long)row * G + g) * H)[c] = pack8(d);
       }
     }
@@ -175,13 +175,13 @@ static int pick_vpl(int nvec) {
 }
 
 bool rmsnorm_fwd_warp(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr24, float inv_keep, cudaStream_t s) {
+                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, cudaStream_t s) {
   const int vpl = pick_vpl(H / 8);
   if (vpl == 0) return false;
   const int grid = ceil_div(M, kWarpsPerBlock);
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)w;
   bf16 *yp = (bf16*)y, *xdp = (bf16*)xd;
-#define L(V) rmsnorm_fwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, keys, thr24, inv_keep)
+#define L(V) rmsnorm_fwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, keys, thr16, inv_keep)
   switch (vpl) {
     case 1: L(1); break;
     case 2: L(2); break;

@@ -64,12 +64,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  // Slow path.  The watchdog clock is only consulted every 64 K failed polls (try_wait itself suspends the thread for a
+  // hardware-defined interval): reading %globaltimer costs on the order of a microsecond, and paying that on every
+  // not-yet-satisfied wait put ~6 us of pure latency on each output tile (measured: K=128 GEMM 36 us -> see profiles/).
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3fff) == 0 && global_timer_ns() - t0 > SM100_WATCHDOG_NS) {
-      printf("sm100 watchdog: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0xffffu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > SM100_WATCHDOG_NS) {
+        printf("sm100 watchdog: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

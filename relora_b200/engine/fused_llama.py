@@ -242,6 +242,7 @@ class FusedLlamaStepper:
         self._attn_saved: List = []
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
         self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
+        self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "2304"))  # stacked output width from which dx uses two kernels
         self._wg_done: Dict[str, torch.cuda.Event] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -417,8 +418,15 @@ class FusedLlamaStepper:
                 done.record()
             self._wg_done[tag] = done
         if self.fused_dx:
-            # one kernel: out = dy·W + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)  (1+G accumulators in tensor memory, masks in the epilogue)
-            C.lora_dx(dy, S_W, du, S_A, out, self.seed if drop else None, list(keys) if drop else [0] * G, self.p if drop else 0.0)
+            sd, ks, pp = (self.seed, list(keys), self.p) if drop else (None, [0] * G, 0.0)
+            if G * Ng >= self.dx_split_k:
+                # long reductions: the frozen-path product runs on the 256-wide / CTA-pair GEMM (1.3-1.5x the per-FLOP rate of
+                # the 128-wide multi-accumulator tiles), then one light pass adds the masked low-rank terms
+                g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
+                C.lora_dx(None, None, du, S_A, out, sd, ks, pp, base_out)
+            else:
+                # one kernel: out = dy·W + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)  (1+G accumulators in tensor memory, masks in the epilogue)
+                C.lora_dx(dy, S_W, du, S_A, out, sd, ks, pp)
         else:
             # frozen path: base = dy · W     (W stacked [G·Ng, K], read MN-major)
             g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)

@@ -12,8 +12,8 @@ import torch
 import torch.nn.functional as F
 
 # ----------------------------------------------------------------------------- dropout mask
-# Counter-based keep-mask shared bit-for-bit by the CUDA kernels (csrc/common.cuh: keep_bit()).
-# keep(row, col) = (lowbias32(row*C1 ^ col*C2 ^ seed) >> 8) >= round(p * 2^24)
+# Counter-based keep-mask shared bit-for-bit by the CUDA kernels (csrc/common.cuh: keep_drop()).
+# h = lowbias32(row*C1 ^ (col>>1)*C2 ^ seed);  keep(row, col) = ((col & 1) ? h >> 16 : h & 0xFFFF) >= round(p * 2^16)
 _C1 = 0x9E3779B1
 _C2 = 0x85EBCA77
 _M32 = 0xFFFFFFFF
@@ -30,15 +30,27 @@ def _lowbias32(x: torch.Tensor) -> torch.Tensor:
 
 
 def dropout_threshold(p: float) -> int:
-    return int(round(p * (1 << 24)))
+    """16-bit keep threshold (see :func:`dropout_keep_mask`)."""
+    return int(round(p * (1 << 16)))
 
 
 def dropout_keep_mask(seed: int, rows: int, cols: int, p: float, device=None, row_offset: int = 0, col_offset: int = 0) -> torch.Tensor:
     """Boolean ``[rows, cols]`` keep mask for dropout probability ``p`` and 32-bit ``seed``."""
     r = torch.arange(row_offset, row_offset + rows, dtype=torch.int64, device=device).unsqueeze(1)
     c = torch.arange(col_offset, col_offset + cols, dtype=torch.int64, device=device).unsqueeze(0)
-    x = ((r * _C1) & _M32) ^ ((c * _C2) & _M32) ^ (int(seed) & _M32)
-    return (_lowbias32(x) >> 8) >= dropout_threshold(p)
+    # one 32-bit hash per column pair, its halves compared against a 16-bit threshold (csrc/common.cuh:keep_drop)
+    x = ((r * _C1) & _M32) ^ (((c >> 1) * _C2) & _M32) ^ (int(seed) & _M32)
+    h = _lowbias32(x)
+    half = torch.where((c & 1) == 1, h >> 16, h & 0xFFFF)
+    return half >= dropout_threshold(p)
+
+
+def random_prune_keep_mask(seed: int, n: int, ratio: float, device=None, offset: int = 0) -> torch.Tensor:
+    """Keep mask of the hash-based random pruning of ``n`` consecutive elements starting at flat index ``offset``
+    (one 24-bit draw per element; ``csrc/optim.cu:random_prune_kernel`` / ``common.cuh:keep_bit``)."""
+    c = torch.arange(offset, offset + n, dtype=torch.int64, device=device)
+    x = ((c * _C2) & _M32) ^ (int(seed) & _M32)
+    return (_lowbias32(x) >> 8) >= int(round(ratio * (1 << 24)))
 
 
 def mix_seed(base: int, *keys: int) -> int:

@@ -302,7 +302,7 @@ class FlatAdamW(torch.optim.Optimizer):
                     if self._native is not None and seg.is_cuda:
                         self._native.random_prune_(seg, ratio, s, a - o)
                     else:
-                        keep = ref.dropout_keep_mask(s, 1, b - a, ratio, device=seg.device, col_offset=a - o)[0]
+                        keep = ref.random_prune_keep_mask(s, b - a, ratio, device=seg.device, offset=a - o)
                         seg.mul_(keep.to(seg.dtype))
                 else:
                     if self.is_sharded and (a != o or b != o + n):
