@@ -91,7 +91,7 @@ def main():
         if kw.get("residual") is not None:
             by += 2.0 * M * N
         tag = "gemm M%d N%d K%d%s %s%s%s%s%s" % (
-            M, N, K1, "+%d" % K2 if K2 else "", "A^T " if kw.get("a1_mn") else "", "B^T " if not kw.get("b1_mn") else "",
+            M, N, K1, "+%d" % K2 if K2 else "", "A:mn " if kw.get("a1_mn") else "", "B:mn " if kw.get("b1_mn") else "",
             "G%d " % G if G > 1 else "", "acc32 " if kw.get("accumulate") and out.dtype == torch.float32 else "",
             "+res" if kw.get("residual") is not None else "")
         n0 = C.launch_count()
@@ -115,8 +115,18 @@ def main():
                 dn = self._inner.launch_count() - n0
                 if dn:
                     by = tensor_bytes(args, kw)
+                    tag, fl = name, 0.0
+                    if name == "lora_dx":
+                        dy, w, du, aa, out = args[:5]
+                        base = args[8] if len(args) > 8 else kw.get("base")
+                        G = len(args[6])
+                        Mx, N = out.shape
+                        Kb = 0 if base is not None else dy.shape[1]
+                        fl = 2.0 * Mx * N * (Kb + du.shape[1])
+                        by = 2.0 * (Mx * Kb + Kb * N + Mx * du.shape[1] + du.shape[1] * N + Mx * N * (2 if base is not None else 1))
+                        tag = "lora_dx M%d N%d Kb%d G%d%s" % (Mx, N, Kb, G, " (+base)" if base is not None else "")
                     for _ in range(dn):
-                        tags.append((name, 0.0, by / dn))
+                        tags.append((tag, fl / dn, by / dn))
                 return r
 
             return wrapped

@@ -242,7 +242,7 @@ class FusedLlamaStepper:
         self._attn_saved: List = []
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
         self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
-        self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "2304"))  # stacked output width from which dx uses two kernels
+        self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "2048"))  # stacked output width from which dx uses two kernels
         self._wg_done: Dict[str, torch.cuda.Event] = {}
 
     # ------------------------------------------------------------------ plumbing
