@@ -1,0 +1,706 @@
+// Causal flash attention for sm_100a: tcgen05 MMAs with fp32 scores / outputs in tensor memory, TMA loads straight out of
+// the packed qkv projection buffer, one query (or key) row per thread so row statistics need no shuffles.
+//
+// Replaces the reference's F.scaled_dot_product_attention call (peft_pretraining/modeling_llama.py:241-247 and
+// modeling_pythia.py attention) for head_dim <= 64.  Three kernels:
+//
+//   attn_fwd_kernel      CTA = (128 queries, head, batch); per 64 keys:  S = Q·Kᵀ -> online softmax -> O += P·V
+//   attn_bwd_dq_kernel   CTA = (128 queries, head, batch); per 64 keys:  S, dP = dO·Vᵀ -> dS -> dQ += dS·K
+//   attn_bwd_dkv_kernel  CTA = (128 keys, head, batch); per 64 queries:  Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ -> Pᵀ, dSᵀ -> dV += Pᵀ·dO, dK += dSᵀ·Q
+//
+// Roles inside a CTA: warps 0-3 = 128 "row" threads (thread i <-> TMEM lane i), warp 4 lane 0 = TMA + MMA issue.
+// Shared-memory tiles are 64 columns (128 bytes) wide with the 128-byte swizzle, so the same [64 x 64] tile serves as a K-major
+// operand (reduction over head_dim) and as an MN-major operand (reduction over its rows) by descriptor alone.
+#include <cuda.h>
+
+#include <mutex>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "attention.h"
+#include "common.cuh"
+#include "sm100.cuh"
+#include "tensormap.h"
+
+namespace rb {
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BQ = 128;  // rows owned by the row threads (queries in fwd / dq, keys in dkv)
+constexpr int BK = 64;   // columns per step (keys in fwd / dq, queries in dkv)
+constexpr int kTile128 = 128 * 128;  // bytes of a [128 x 64] bf16 tile
+constexpr int kTile64 = 64 * 128;    // bytes of a [64 x 64] bf16 tile
+constexpr int kThreads = 160;
+constexpr float kNegInf = -1e30f;
+
+__device__ __forceinline__ uint64_t desc_k(const uint8_t* tile, int kstep) {  // K-major operand, 16 columns per MMA
+  return make_desc_sw128(smem_u32(tile) + kstep * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mn(const uint8_t* tile, int kstep) {  // MN-major operand, 16 rows per MMA
+  return make_desc_sw128(smem_u32(tile) + kstep * 2048, 8192, 1024);
+}
+
+// row `r` of a [128 x 64] bf16 tile (128-byte swizzle): 8 chunks of 8 values
+__device__ __forceinline__ void store_row64(uint8_t* tile, int r, const float* v) {
+  uint8_t* rowp = tile + r * 128;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v[q * 8 + i];
+    *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = pack8(f);
+  }
+}
+
+__device__ __forceinline__ void ld64(uint32_t taddr, float* v) {  // 64 fp32 columns of this thread's TMEM lane
+  uint32_t a[32], b[32];
+  tmem_ld_32x32b_x32(taddr, a);
+  tmem_ld_32x32b_x32(taddr + 32, b);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(a[i]);
+    v[32 + i] = __uint_as_float(b[i]);
+  }
+}
+
+struct FwdArgs {
+  long long* trace;  // diagnostics: clock64 stamps of the heaviest CTA (bench/attn_trace.py); normally null
+  bf16* out;
+  long long ld_out;
+  float* lse;
+  int B, T, nh, hd;
+  float scale_log2;
+};
+
+// =============================================================================================== forward
+__global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTile128;      // 2 stages
+  uint8_t* sV = sK + 2 * kTile64;   // 2 stages
+  uint8_t* sP = sV + 2 * kTile64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTile128);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_free = bars + 3;
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // long (late) query blocks first
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int t0 = qb * BQ;
+  const int kv_end = min(p.T, t0 + BQ);
+  const int n_kv = (kv_end + BK - 1) / BK;
+  const int row0 = b * p.T;
+
+  if (threadIdx.x == 128) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_free[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_qkv);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 128);  // S: columns 0-63, O partial: columns 64-127
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_kv = [&](int jj, int st) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
+        tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
+        tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK);
+      };
+      mbar_arrive_expect_tx(q_full, kTile128);
+      tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
+      tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64);
+      load_kv(0, 0);
+      if (n_kv > 1) load_kv(1, 1);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      auto issue_s = [&](int st) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_s, k != 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int jj = 0; jj < n_kv; ++jj) {
+        const int st = jj & 1;
+        mbar_wait(p_ready, jj & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + 64, desc_k(sP, k), desc_mn(sV + st * kTile64, k), idesc_pv, (jj | k) != 0);  // O accumulates in TMEM
+        umma_commit(&kv_free[st]);
+        if (jj + 1 < n_kv) {
+          mbar_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(st ^ 1);  // its commit also covers the P·V above: s_full(j+1) => O holds steps <= j and P is free again
+        } else {
+          umma_commit(o_full);
+        }
+        if (jj + 2 < n_kv) {
+          mbar_wait(&kv_free[st], (jj >> 1) & 1);
+          load_kv(jj + 2, st);
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int t = t0 + r;
+    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    // The output accumulates in tensor memory across key steps.  The running maximum used for the exponentials ("m") is
+    // only raised -- and O rescaled by a TMEM load / multiply / store -- when a step's maximum exceeds it by more than
+    // 2^8; any reference maximum is mathematically valid as long as exp2 stays in range, and the same m enters l.
+    float m = kNegInf, l = 0.f;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+#define ATR(slot) do { if (tr) p.trace[(slot) * 64 + jj] = clock64(); } while (0)
+    if (tr) p.trace[7 * 64] = clock64();
+    for (int jj = 0; jj < n_kv; ++jj) {
+      const int k0 = jj * BK;
+      ATR(0);
+      mbar_wait(s_full, jj & 1);
+      tc_fence_after();
+      ATR(1);
+      float s[64];
+      ld64(lane_addr, s);
+      ATR(2);
+      const bool edge = (k0 + BK - 1 > t0) || (k0 + BK > p.T);  // diagonal block or ragged tail (uniform in the CTA)
+      float mx = kNegInf;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float v = s[c] * p.scale_log2;
+        if (edge && (k0 + c > t || k0 + c >= p.T)) v = kNegInf;
+        s[c] = v;
+        mx = fmaxf(mx, v);
+      }
+      if (jj == 0) {
+        m = mx;  // first step: P·V overwrites O (accumulate = 0), nothing to rescale
+      } else if (__any_sync(0xffffffffu, mx > m + 8.0f)) {
+        // rare: bring this warp's rows of O (complete through step jj-1, see issue_s) to the new reference maximum
+        const float m_new = fmaxf(m, mx);
+        const float f = exp2f(m - m_new);
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(lane_addr + 64, o0);
+        tmem_ld_32x32b_x32(lane_addr + 96, o1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          o0[i] = __float_as_uint(__uint_as_float(o0[i]) * f);
+          o1[i] = __float_as_uint(__uint_as_float(o1[i]) * f);
+        }
+        tmem_st_32x32b_x32(lane_addr + 64, o0);
+        tmem_st_32x32b_x32(lane_addr + 96, o1);
+        tmem_st_wait();
+        l *= f;
+        m = m_new;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float e = exp2f(s[c] - m);
+        s[c] = e;
+        sum += e;
+      }
+      l += sum;
+      ATR(3);
+      store_row64(sP, r, s);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      ATR(4);
+    }
+#undef ATR
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    float O[64];
+    ld64(lane_addr + 64, O);
+    if (t < p.T) {
+      const float inv = 1.0f / l;
+      bf16* op = p.out + (long long)(row0 + t) * p.ld_out + head * p.hd;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q * 8 < p.hd) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = O[q * 8 + i] * inv;
+          *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
+        }
+      }
+      p.lse[((long long)b * p.nh + head) * p.T + t] = m + log2f(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// =============================================================================================== backward: delta
+// delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ld_o, const bf16* __restrict__ dout,
+                                                         long long ld_do, float* __restrict__ delta, int B, int T, int nh, int hd) {
+  const long long total = (long long)B * T * nh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int h = int(i % nh);
+    const long long row = i / nh;
+    const bf16* a = o + row * ld_o + h * hd;
+    const bf16* g = dout + row * ld_do + h * hd;
+    float acc = 0.f;
+    for (int q = 0; q < hd; q += 8) {
+      float x[8], y[8];
+      unpack8(*reinterpret_cast<const uint4*>(a + q), x);
+      unpack8(*reinterpret_cast<const uint4*>(g + q), y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += x[j] * y[j];
+    }
+    const long long bb = row / T, t = row % T;
+    delta[(bb * nh + h) * T + t] = acc;
+  }
+}
+
+struct BwdArgs {
+  const float* lse;
+  const float* delta;
+  bf16* dqkv;
+  long long ld_dqkv;
+  int B, T, nh, hd;
+  float scale, scale_log2;
+};
+
+// =============================================================================================== backward: dQ
+__global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                   const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + kTile128;
+  uint8_t* sK = sdO + kTile128;     // 2 stages
+  uint8_t* sV = sK + 2 * kTile64;   // 2 stages
+  uint8_t* sdS = sV + 2 * kTile64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + kTile128);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_free = bars + 3;
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int t0 = qb * BQ;
+  const int kv_end = min(p.T, t0 + BQ);
+  const int n_kv = (kv_end + BK - 1) / BK;
+  const int row0 = b * p.T;
+
+  if (threadIdx.x == 128) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_free[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_ready, 128);
+    mbar_init(dq_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 256);  // S: 0-63, dP: 64-127, dQ: 128-191
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_kv = [&](int jj, int st) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
+        tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
+        tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK);
+      };
+      mbar_arrive_expect_tx(q_full, 2 * kTile128);
+      tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
+      tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64);
+      tma_load_3d(&map_do, q_full, sdO, 0, head, row0 + t0);
+      tma_load_3d(&map_do, q_full, sdO + kTile64, 0, head, row0 + t0 + 64);
+      load_kv(0, 0);
+      if (n_kv > 1) load_kv(1, 1);
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, 0, 1);
+      auto issue_sdp = [&](int st) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_kk, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sdO, k), desc_k(sV + st * kTile64, k), idesc_kk, k != 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0);
+      for (int jj = 0; jj < n_kv; ++jj) {
+        const int st = jj & 1;
+        mbar_wait(ds_ready, jj & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + 128, desc_k(sdS, k), desc_mn(sK + st * kTile64, k), idesc_kmn, (jj | k) != 0);
+        umma_commit(&kv_free[st]);
+        if (jj + 1 < n_kv) {
+          mbar_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_sdp(st ^ 1);  // its commit also covers the dQ MMAs above: dS may be overwritten once sdp_full fires
+        } else {
+          umma_commit(dq_full);
+        }
+        if (jj + 2 < n_kv) {
+          mbar_wait(&kv_free[st], (jj >> 1) & 1);
+          load_kv(jj + 2, st);
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int t = t0 + r;
+    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    const long long stat = ((long long)b * p.nh + head) * p.T + t;
+    const float lse = t < p.T ? p.lse[stat] : 0.f;
+    const float dl = t < p.T ? p.delta[stat] : 0.f;
+    for (int jj = 0; jj < n_kv; ++jj) {
+      const int k0 = jj * BK;
+      mbar_wait(sdp_full, jj & 1);
+      tc_fence_after();
+      float s[64], dp[64];
+      ld64(lane_addr, s);
+      ld64(lane_addr + 64, dp);
+      const bool edge = (k0 + BK - 1 > t0) || (k0 + BK > p.T);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float pr = exp2f(s[c] * p.scale_log2 - lse);
+        if (edge && (k0 + c > t || k0 + c >= p.T)) pr = 0.f;
+        s[c] = pr * (dp[c] - dl) * p.scale;
+      }
+      store_row64(sdS, r, s);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+    }
+    mbar_wait(dq_full, 0);
+    tc_fence_after();
+    float dq[64];
+    ld64(lane_addr + 128, dq);
+    if (t < p.T) {
+      bf16* op = p.dqkv + (long long)(row0 + t) * p.ld_dqkv + head * p.hd;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q * 8 < p.hd) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = dq[q * 8 + i];
+          *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =============================================================================================== backward: dK, dV
+__global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                    const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kTile128;
+  uint8_t* sQ = sV + kTile128;      // 2 stages of [64 queries x 64]
+  uint8_t* sdO = sQ + 2 * kTile64;  // 2 stages
+  uint8_t* sPt = sdO + 2 * kTile64;
+  uint8_t* sdSt = sPt + kTile128;
+  float* s_lse = reinterpret_cast<float*>(sdSt + kTile128);  // [2][64]
+  float* s_dl = s_lse + 128;                                  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dl + 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_free = bars + 3;
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_ready = bars + 6;
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x;  // early key blocks see the most queries and are scheduled first
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kstart = kb * BQ;
+  const int n_q = (p.T - kstart + BK - 1) / BK;  // query steps of 64 starting at the block's first key
+  const int row0 = b * p.T;
+
+  if (threadIdx.x == 128) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 128);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 256);  // Sᵀ: 0-63, dPᵀ: 64-127, dV: 128-191, dK: 192-255
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_q = [&](int ii, int st) {
+        mbar_arrive_expect_tx(&q_full[st], 2 * kTile64);
+        tma_load_3d(&map_qkv, &q_full[st], sQ + st * kTile64, 0, head, row0 + kstart + ii * BK);
+        tma_load_3d(&map_do, &q_full[st], sdO + st * kTile64, 0, head, row0 + kstart + ii * BK);
+      };
+      mbar_arrive_expect_tx(kv_full, 2 * kTile128);
+      tma_load_3d(&map_qkv, kv_full, sK, 0, p.nh + head, row0 + kstart);
+      tma_load_3d(&map_qkv, kv_full, sK + kTile64, 0, p.nh + head, row0 + kstart + 64);
+      tma_load_3d(&map_qkv, kv_full, sV, 0, 2 * p.nh + head, row0 + kstart);
+      tma_load_3d(&map_qkv, kv_full, sV + kTile64, 0, 2 * p.nh + head, row0 + kstart + 64);
+      load_q(0, 0);
+      if (n_q > 1) load_q(1, 1);
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, 0, 1);
+      auto issue_sdp = [&](int st) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sK, k), desc_k(sQ + st * kTile64, k), idesc_kk, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sV, k), desc_k(sdO + st * kTile64, k), idesc_kk, k != 0);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0);
+      for (int ii = 0; ii < n_q; ++ii) {
+        const int st = ii & 1;
+        mbar_wait(pds_ready, ii & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + 128, desc_k(sPt, k), desc_mn(sdO + st * kTile64, k), idesc_kmn, (ii | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + 192, desc_k(sdSt, k), desc_mn(sQ + st * kTile64, k), idesc_kmn, (ii | k) != 0);
+        umma_commit(&q_free[st]);
+        if (ii + 1 < n_q) {
+          mbar_wait(&q_full[st ^ 1], ((ii + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_sdp(st ^ 1);
+        } else {
+          umma_commit(acc_full);
+        }
+        if (ii + 2 < n_q) {
+          mbar_wait(&q_free[st], (ii >> 1) & 1);
+          load_q(ii + 2, st);
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int kk = kstart + r;  // this thread's key
+    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    const long long stat0 = ((long long)b * p.nh + head) * p.T;
+    for (int ii = 0; ii < n_q; ++ii) {
+      const int q0 = kstart + ii * BK;
+      {  // stage the 64 queries' lse / delta (double buffered; the barrier below orders reuse)
+        const int c = r & 63;
+        const int tq = q0 + c;
+        float* dst = (r < 64 ? s_lse : s_dl) + (ii & 1) * 64;
+        const float* src = r < 64 ? p.lse : p.delta;
+        dst[c] = tq < p.T ? src[stat0 + tq] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      const float* lse = s_lse + (ii & 1) * 64;
+      const float* dl = s_dl + (ii & 1) * 64;
+      mbar_wait(sdp_full, ii & 1);
+      tc_fence_after();
+      float s[64], dp[64];
+      ld64(lane_addr, s);
+      ld64(lane_addr + 64, dp);
+      const bool edge = (q0 < kstart + BQ) || (q0 + BK > p.T) || (kstart + BQ > p.T);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const int tq = q0 + c;
+        float pr = exp2f(s[c] * p.scale_log2 - lse[c]);
+        if (edge && (kk > tq || tq >= p.T || kk >= p.T)) pr = 0.f;
+        s[c] = pr;
+        dp[c] = pr * (dp[c] - dl[c]) * p.scale;
+      }
+      store_row64(sPt, r, s);
+      store_row64(sdSt, r, dp);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float acc[64];
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {  // 0: dV -> v slot, 1: dK -> k slot
+      ld64(lane_addr + 128 + which * 64, acc);
+      if (kk < p.T) {
+        bf16* op = p.dqkv + (long long)(row0 + kk) * p.ld_dqkv + (long long)((which == 0 ? 2 : 1) * p.nh + head) * p.hd;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 8 < p.hd) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = acc[q * 8 + i];
+            *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+struct HeadMapKey {
+  const void* ptr;
+  long long ld, rows;
+  int hd, heads;
+  bool operator==(const HeadMapKey& o) const { return ptr == o.ptr && ld == o.ld && rows == o.rows && hd == o.hd && heads == o.heads; }
+};
+struct HeadMapHash {
+  size_t operator()(const HeadMapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= std::hash<long long>()(k.ld * 1315423911ll + k.rows) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h ^= std::hash<long long>()(((long long)k.hd << 32) | (unsigned)k.heads) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+std::unordered_map<HeadMapKey, CUtensorMap, HeadMapHash> g_head_maps;
+std::mutex g_head_maps_mu;
+
+// [rows, heads*hd] bf16 (row stride ld) viewed as [hd, heads, rows]; box = 64 x 1 x 64 rows
+CUtensorMap head_map(const void* ptr, long long ld, long long rows, int hd, int heads) {
+  HeadMapKey key{ptr, ld, rows, hd, heads};
+  {
+    std::lock_guard<std::mutex> lk(g_head_maps_mu);
+    auto it = g_head_maps.find(key);
+    if (it != g_head_maps.end()) return it->second;
+  }
+  CUtensorMap m = make_map_3d_bf16(ptr, hd, heads, rows, hd, ld, 64, 1, 64);
+  std::lock_guard<std::mutex> lk(g_head_maps_mu);
+  if (g_head_maps.size() > 4096) g_head_maps.clear();
+  g_head_maps.emplace(key, m);
+  return m;
+}
+
+void check_shape(int B, int T, int nh, int hd) {
+  if (B <= 0 || T <= 0 || nh <= 0) throw std::runtime_error("attention: empty problem");
+  if (hd % 8 != 0 || hd > 64) throw std::runtime_error("attention: head_dim must be a multiple of 8 and <= 64");
+}
+
+constexpr int kFwdSmem = kTile128 + 4 * kTile64 + kTile128 + 256 + 1024;
+constexpr int kDqSmem = 2 * kTile128 + 4 * kTile64 + kTile128 + 256 + 1024;
+constexpr int kDkvSmem = 2 * kTile128 + 4 * kTile64 + 2 * kTile128 + 1024 + 256 + 1024;
+
+void* g_attn_trace = nullptr;
+
+}  // namespace
+
+void attention_set_trace(void* buf) { g_attn_trace = buf; }
+
+void attention_fwd(const AttnDesc& d, cudaStream_t stream) {
+  check_shape(d.B, d.T, d.nh, d.hd);
+  const long long rows = (long long)d.B * d.T;
+  CUtensorMap map = head_map(d.qkv, d.ld_qkv, rows, d.hd, 3 * d.nh);
+  static bool configured = false;
+  if (!configured) {
+    check(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), "cudaFuncSetAttribute(attn_fwd)");
+    configured = true;
+  }
+  FwdArgs p;
+  p.trace = reinterpret_cast<long long*>(g_attn_trace);
+  p.out = reinterpret_cast<bf16*>(d.out); p.ld_out = d.ld_out; p.lse = d.lse;
+  p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
+  p.scale_log2 = d.scale * 1.4426950408889634f;
+  dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
+  attn_fwd_kernel<<<grid, kThreads, kFwdSmem, stream>>>(map, p);
+  RB_CHECK_LAUNCH("attn_fwd_kernel");
+}
+
+void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
+  check_shape(d.B, d.T, d.nh, d.hd);
+  const long long rows = (long long)d.B * d.T;
+  CUtensorMap map_qkv = head_map(d.qkv, d.ld_qkv, rows, d.hd, 3 * d.nh);
+  CUtensorMap map_do = head_map(d.dout, d.ld_dout, rows, d.hd, d.nh);
+  static bool configured = false;
+  if (!configured) {
+    check(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem), "cudaFuncSetAttribute(attn_dq)");
+    check(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem), "cudaFuncSetAttribute(attn_dkv)");
+    configured = true;
+  }
+  {
+    const long long total = rows * d.nh;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+    attn_delta_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d.out), d.ld_out, reinterpret_cast<const bf16*>(d.dout),
+                                                d.ld_dout, d.delta, d.B, d.T, d.nh, d.hd);
+    RB_CHECK_LAUNCH("attn_delta_kernel");
+  }
+  BwdArgs p;
+  p.lse = d.lse; p.delta = d.delta; p.dqkv = reinterpret_cast<bf16*>(d.dqkv); p.ld_dqkv = d.ld_dqkv;
+  p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
+  p.scale = d.scale; p.scale_log2 = d.scale * 1.4426950408889634f;
+  dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
+  attn_bwd_dkv_kernel<<<grid, kThreads, kDkvSmem, stream>>>(map_qkv, map_do, p);
+  RB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+  attn_bwd_dq_kernel<<<grid, kThreads, kDqSmem, stream>>>(map_qkv, map_do, p);
+  RB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+}
+
+}  // namespace rb

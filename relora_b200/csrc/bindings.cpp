@@ -5,6 +5,7 @@
 #include <torch/extension.h>
 
 #include "comm.h"
+#include "attention.h"
 #include "gemm.h"
 #include "kernels.h"
 
@@ -201,6 +202,35 @@ void lora_dx(const OptTensor& dy, const OptTensor& w, const Tensor& du, const Te
   for (int i = 0; i < G; ++i) d.seed_key[i] = (uint32_t)keys[i];
   c10::cuda::CUDAGuard guard(out.device());
   rb::lora_dx(d, cur_stream());
+}
+
+// causal flash attention over the packed (post-RoPE) qkv buffer [B*T, 3*nh*hd]
+void attention_fwd(const Tensor& qkv, Tensor& out, Tensor& lse, int64_t B, int64_t T, int64_t nh, int64_t hd, double scale) {
+  chk_bf16(qkv, "qkv"); chk_bf16(out, "out"); chk_2d_rowmajor(qkv, "qkv"); chk_2d_rowmajor(out, "out");
+  TORCH_CHECK(qkv.size(0) == B * T && qkv.size(1) == 3 * nh * hd, "qkv must be [B*T, 3*nh*hd]");
+  TORCH_CHECK(out.size(0) == B * T && out.size(1) == nh * hd, "out must be [B*T, nh*hd]");
+  TORCH_CHECK(lse.is_cuda() && lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == B * nh * T, "lse must be fp32 [B, nh, T]");
+  rb::AttnDesc d;
+  d.qkv = qkv.data_ptr(); d.ld_qkv = qkv.stride(0); d.out = out.data_ptr(); d.ld_out = out.stride(0); d.lse = lse.data_ptr<float>();
+  d.B = (int)B; d.T = (int)T; d.nh = (int)nh; d.hd = (int)hd; d.scale = (float)scale;
+  c10::cuda::CUDAGuard guard(qkv.device());
+  rb::attention_fwd(d, cur_stream());
+}
+void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, const Tensor& lse, Tensor& delta, Tensor& dqkv, int64_t B,
+                   int64_t T, int64_t nh, int64_t hd, double scale) {
+  chk_bf16(qkv, "qkv"); chk_bf16(out, "out"); chk_bf16(dout, "dout"); chk_bf16(dqkv, "dqkv");
+  chk_2d_rowmajor(qkv, "qkv"); chk_2d_rowmajor(out, "out"); chk_2d_rowmajor(dout, "dout"); chk_2d_rowmajor(dqkv, "dqkv");
+  TORCH_CHECK(qkv.size(0) == B * T && qkv.size(1) == 3 * nh * hd && dqkv.size(0) == B * T && dqkv.size(1) == 3 * nh * hd, "qkv / dqkv must be [B*T, 3*nh*hd]");
+  TORCH_CHECK(out.size(0) == B * T && out.size(1) == nh * hd && dout.size(0) == B * T && dout.size(1) == nh * hd, "out / dout must be [B*T, nh*hd]");
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == B * nh * T, "lse must be fp32 [B, nh, T]");
+  TORCH_CHECK(delta.is_cuda() && delta.scalar_type() == at::kFloat && delta.is_contiguous() && delta.numel() == B * nh * T, "delta must be fp32 [B, nh, T]");
+  rb::AttnBwdDesc d;
+  d.qkv = qkv.data_ptr(); d.ld_qkv = qkv.stride(0); d.out = out.data_ptr(); d.ld_out = out.stride(0);
+  d.dout = dout.data_ptr(); d.ld_dout = dout.stride(0); d.lse = lse.data_ptr<float>(); d.delta = delta.data_ptr<float>();
+  d.dqkv = dqkv.data_ptr(); d.ld_dqkv = dqkv.stride(0);
+  d.B = (int)B; d.T = (int)T; d.nh = (int)nh; d.hd = (int)hd; d.scale = (float)scale;
+  c10::cuda::CUDAGuard guard(qkv.device());
+  rb::attention_bwd(d, cur_stream());
 }
 
 void rope_inplace(Tensor& buf, int64_t T, int64_t n_rot_heads, int64_t hd, int64_t rotary_dim, const Tensor& cos, const Tensor& sin,
@@ -406,6 +436,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
   m.def("dropout_expand", &dropout_expand);
   m.def("dropout_combine", &dropout_combine);
+  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_set_trace", [](const OptTensor& t) {
+    if (!t.has_value()) { rb::attention_set_trace(nullptr); return; }
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 8 * 64, "trace buffer: int64 CUDA tensor of >= 512 elements");
+    rb::attention_set_trace(t->data_ptr());
+  });
+  m.def("attention_bwd", &attention_bwd);
   m.def("lora_dx", &lora_dx, py::arg("dy"), py::arg("w"), py::arg("du"), py::arg("a"), py::arg("out"), py::arg("seed"), py::arg("keys"),
         py::arg("p"), py::arg("base") = py::none());
   m.def("rope_inplace", &rope_inplace);

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "tensormap.h"
 #include "sm100.cuh"
 
 namespace rb {
@@ -951,6 +952,32 @@ static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer
   std::lock_guard<std::mutex> lk(g_maps_mu);
   if (g_maps.size() > 8192) g_maps.clear();  // eager runs see fresh activation pointers every step: bound the cache
   g_maps.emplace(key, m);
+  return m;
+}
+
+// 3-D bf16 tensor map (128B swizzle, zero fill outside the tensor): dims d0 (contiguous) x d1 x d2 with strides s1 / s2 elements.
+// Attention views the packed [rows, 3*hidden] qkv buffer as [head_dim, heads, rows]; a 64-wide box over a 48-wide head is
+// zero padded by the TMA unit.
+CUtensorMap make_map_3d_bf16(const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1,
+                             int b2) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (s1 * 2) % 16 != 0 || (s2 * 2) % 16 != 0)
+    throw std::runtime_error("tensor map: base and strides must be 16-byte aligned");
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    int dev = 0;  // bind the primary context on this thread (legal during stream capture), then retry
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    check(cudaSetDevice(dev), "cudaSetDevice");
+  }
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(3d) failed with code " + std::to_string((int)r));
   return m;
 }
 

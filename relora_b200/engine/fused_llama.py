@@ -78,7 +78,7 @@ class FusedLlamaStepper:
     def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
                  transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096,
-                 overlap_wgrad: bool = True):
+                 overlap_wgrad: bool = True, attention: str = "auto"):
         ok, why = supports(model)
         if not ok:
             raise RuntimeError(why)
@@ -240,6 +240,14 @@ class FusedLlamaStepper:
         self._replays = 0
         self._launches_per_micro = 0
         self._attn_saved: List = []
+        attention = os.environ.get("RELORA_B200_ATTENTION", attention)
+        native_ok = self.hd % 8 == 0 and self.hd <= 64
+        if attention == "native" and not native_ok:
+            raise RuntimeError(f"--attention native supports head_dim <= 64 (multiple of 8), got {self.hd}")
+        # auto: torch SDPA (cuDNN's sm100 flash kernels) while it is the faster of the two -- measured on B200 (bench/attn_bench.py):
+        # forward 80 vs 48 us, backward 222 vs 137 us at B 24 x T 512 x 16 heads x 48; the tcgen05 kernels are selected with
+        # --attention native (tests/test_kernels_gpu.py::test_attention_fwd_bwd, test_native_attention_matches_sdpa_in_the_executor)
+        self.native_attn = attention == "native"
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
         self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
         self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "2048"))  # stacked output width from which dx uses two kernels
@@ -285,6 +293,10 @@ class FusedLlamaStepper:
         self.dgu = e(M, 2 * f)
         self.dhmid, self.dhmid2 = e(M, f), e(M, f)
         self.du_bufs = {"d": e(M, r), "gu": e(M, 2 * r), "o": e(M, r), "qkv": e(M, 3 * r)}
+        if self.native_attn:
+            self.attn_o = e(L, M, h)
+            self.lse = torch.empty(L, B, self.nh, T, dtype=torch.float32, device=dev)
+            self.delta = torch.empty(B, self.nh, T, dtype=torch.float32, device=dev)
         self.parts = e(M, max(3 * h, f))
         ldv = (self.V + 7) // 8 * 8
         self.logits = torch.zeros(min(self.ce_chunk, M), ldv, dtype=BF, device=dev)
@@ -294,8 +306,14 @@ class FusedLlamaStepper:
         self._shape = (B, T)
 
     # ------------------------------------------------------------------ forward + backward of one micro-batch
-    def _attention(self, qkv: torch.Tensor, train: bool):
+    def _attention(self, qkv: torch.Tensor, train: bool, sl: int = 0):
         B, T, nh, hd = self.B_, self.T_, self.nh, self.hd
+        if self.native_attn:
+            # tcgen05 flash attention straight out of the packed projection buffer (csrc/attention.cu); the output and the
+            # log-sum-exp of the layer are what the backward kernels need
+            out = self.attn_o[sl]
+            self.C.attention_fwd(qkv, out, self.lse[sl], B, T, nh, hd, 1.0 / math.sqrt(hd))
+            return out
         v5 = qkv.view(B, T, 3, nh, hd)
         q, k, v = (v5[:, :, i].transpose(1, 2) for i in range(3))
         if train:
@@ -338,7 +356,7 @@ class FusedLlamaStepper:
                 xd = xn
             self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h)
             C.rope_inplace(qkv, self.T_, 2 * self.nh, self.hd, self.hd, self.cos, self.sin, False, 0)
-            attn = self._attention(qkv, train)
+            attn = self._attention(qkv, train, sl)
             if p > 0:
                 xd_o = self.xd_o[sl]
                 C.dropout_expand(attn, xd_o, seed, [S.key_o], p)
@@ -468,10 +486,19 @@ class FusedLlamaStepper:
             # ---- attention: x1 = attn·Woᵀ + u_o·B_oᵀ + x
             self._lora_group_bwd(dx, S.B_o, S.Wo, S.A_o, S.gA_o, S.gB_o, self.xd_o[l], self.u_o[l], [S.key_o],
                                  G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn, tag="o")
-            o, q, k, v = self._attn_saved[l]
-            dq, dk, dv = torch.autograd.grad(o, (q, k, v), self.dattn.view(B, T, nh, hd).transpose(1, 2))
-            self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
-            if dq.stride() == dk.stride() == dv.stride() and dq.stride(3) == 1:
+            if self.native_attn:
+                self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
+                C.attention_bwd(self.qkv[l], self.attn_o[l], self.dattn, self.lse[l], self.delta, self.dqkv, B, T, nh, hd,
+                                1.0 / math.sqrt(hd))
+                C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)  # back through the rotation of q, k
+                dq = None
+            else:
+                o, q, k, v = self._attn_saved[l]
+                dq, dk, dv = torch.autograd.grad(o, (q, k, v), self.dattn.view(B, T, nh, hd).transpose(1, 2))
+                self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
+            if dq is None:
+                pass
+            elif dq.stride() == dk.stride() == dv.stride() and dq.stride(3) == 1:
                 C.rope_pack_bwd(dq, dk, dv, self.dqkv, hd, self.cos, self.sin, 0)  # gather + inverse rotation in one pass
             else:
                 d5 = self.dqkv.view(B, T, 3, nh, hd)

@@ -101,3 +101,28 @@ def test_fused_merge_and_checkpoint_roundtrip(tmp_path, inter):
     sd = w.wrapped_model.state_dict()
     for k, v in w2.wrapped_model.state_dict().items():
         assert torch.equal(v.cpu(), sd[k].cpu()), k
+
+
+def test_native_attention_matches_sdpa_in_the_executor():
+    """The tcgen05 attention kernels and torch SDPA (cuDNN) give the same loss and gradients inside the fused executor."""
+    from relora_b200.engine.fused_llama import FusedLlamaStepper
+    from relora_b200.ops import fused
+
+    dev = torch.device("cuda", 0)
+    wa = _build(0.1)
+    wb = copy.deepcopy(wa)
+    ids = torch.randint(0, 4096, (3, 128), device=dev)
+    fa = FusedLlamaStepper(wa, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=True, attention="native")
+    fb = FusedLlamaStepper(wb, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=False, attention="sdpa")
+    assert fa.native_attn and not fb.native_attn
+    fused.seed_state.set(dev, 77)
+    la = fa.micro_step(ids)
+    fused.seed_state.set(dev, 77)
+    lb = fb.micro_step(ids)
+    assert abs(float(la) - float(lb)) < 2e-2
+    for n, p in zip(fa.trainable_names, fa.trainable_params):
+        ga = fa.store.view_like(fa.store.grads, p).float()
+        gb = fb.store.view_like(fb.store.grads, fb.trainable_params[fa.trainable_names.index(n)]).float()
+        if gb.norm() == 0:
+            continue
+        assert _relerr(ga, gb) < 0.1, n
