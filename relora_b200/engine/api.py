@@ -98,6 +98,8 @@ class TrainingEngine:
             dist.all_reduce(pack)
             mean, skip = pack[0] / dist.get_world_size(), pack[1]
         self.stepper.update(skip=skip)
+        # the fused / flat optimizers step inside update(); mark the wrapped torch counter so LambdaLR does not warn about order
+        self.optimizer._opt_called = True
         self.scheduler.step()
         self.update_step += 1
         self._maybe_reset()
