@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--comm", type=str, default="auto")
     ap.add_argument("--optimizer", type=str, default="adam")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frozen_dtype", type=str, default=None, help="fp8: E4M3 tensor-core path for the frozen weights (opt-in)")
+    ap.add_argument("--attention", type=str, default="auto", choices=["auto", "native", "sdpa"])
     ap.add_argument("--cuda_graphs", type=str, default="true")
     return ap.parse_args()
 
@@ -169,6 +171,7 @@ def run_ours(args):
         relora=5000, cycle_length=5000, scheduler="cosine_restarts", warmup_steps=500, restart_warmup_steps=100,
         lr=1e-3, num_training_steps=20000, reset_optimizer_on_relora=True, dtype="bfloat16", device="cuda",
         engine=args.engine, comm=args.comm, optimizer=args.optimizer, cuda_graphs=args.cuda_graphs.lower() == "true",
+        frozen_dtype=args.frozen_dtype, attention=args.attention,
     )
     dev = info.device
     n_total = args.warmup + args.steps
@@ -203,11 +206,13 @@ def run_ours(args):
             "metric": "training throughput, llama ReLoRA (tokens/s, whole job, device-timed, max over ranks)",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic token ids, random-init weights", "impl": "ours",
+            "dtype": "bf16" if args.frozen_dtype != "fp8" else "bf16 (fp8 E4M3 forward GEMMs of the frozen weights)",
+            "data": "synthetic token ids, random-init weights", "impl": "ours",
             "config": {"model": args.model, "global_batch": args.batch * args.ga * world, "micro_batch_per_gpu": args.batch,
                        "grad_accumulation": args.ga, "seq_len": args.seq, "lora_r": args.lora_r, "lora_dropout": 0.1,
                        "parallelism": f"dp{world}", "optimizer": args.optimizer, "executor": type(eng.stepper).__name__,
                        "comm": getattr(eng.stepper.sync, "transport", "none"),
+                       "attention": "tcgen05 (this repo)" if getattr(eng.stepper, "native_attn", False) else "torch SDPA (cuDNN)",
                        "l2": "per-step working set (weights + activations, >1.5 GB) exceeds the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "native_so": native.so_path(),

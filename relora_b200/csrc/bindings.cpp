@@ -52,12 +52,25 @@ rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
           const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k, int64_t b1_group_kofs,
-          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias, int64_t cta_pair) {
+          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias, int64_t cta_pair, bool fp8,
+          const OptTensor& alpha_dev) {
   c10::cuda::CUDAGuard guard(out.device());
   rb::GemmDesc d;
   d.cta_pair = (int)cta_pair;
-  d.a1 = operand(a1, a1_mn, "a1");
-  d.b1 = operand(b1, b1_mn, "b1");
+  if (fp8) {
+    // E4M3 bytes (torch.uint8 / float8_e4m3fn storage), K-major; leading dimensions in bytes
+    TORCH_CHECK(!a1_mn && !b1_mn, "fp8 operands must be K-major");
+    for (const Tensor* t : {&a1, &b1}) {
+      TORCH_CHECK(t->is_cuda() && t->element_size() == 1 && t->dim() == 2 && t->stride(1) == 1, "fp8 operands: 2-D one-byte CUDA tensors");
+    }
+    d.a1.ptr = a1.data_ptr(); d.a1.ld = a1.stride(0); d.a1.mn_major = false;
+    d.b1.ptr = b1.data_ptr(); d.b1.ld = b1.stride(0); d.b1.mn_major = false;
+    d.fp8 = true;
+  } else {
+    d.a1 = operand(a1, a1_mn, "a1");
+    d.b1 = operand(b1, b1_mn, "b1");
+  }
+  if (alpha_dev.has_value()) d.alpha_dev = f32ptr(alpha_dev);
   d.M = (int)M; d.N = (int)N; d.K1 = (int)K1; d.K2 = (int)K2;
   if (K2 > 0) {
     TORCH_CHECK(a2.has_value() && b2.has_value(), "a2/b2 required when K2 > 0");
@@ -165,6 +178,30 @@ void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, co
   c10::cuda::CUDAGuard guard(out.device());
   rb::dropout_combine(bp, parts.data_ptr(), part_stride, ld_parts, out.data_ptr(), M, H, G, u32ptr(seed), k,
                       (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), cur_stream());
+}
+
+void fp8_quantize_weight(const Tensor& w, Tensor& w8, Tensor& scratch, Tensor& scale, Tensor& inv_scale) {
+  chk_bf16(w, "w"); chk_2d_rowmajor(w, "w");
+  TORCH_CHECK(w8.is_cuda() && w8.element_size() == 1 && w8.dim() == 2 && w8.stride(1) == 1 && w8.sizes() == w.sizes(), "w8: one-byte tensor shaped like w");
+  c10::cuda::CUDAGuard guard(w.device());
+  rb::fp8_quantize_weight(w.data_ptr(), w.stride(0), w8.data_ptr(), w8.stride(0), (int)w.size(0), (int)w.size(1),
+                          const_cast<float*>(f32ptr(scratch)), const_cast<float*>(f32ptr(scale)), const_cast<float*>(f32ptr(inv_scale)),
+                          cur_stream());
+}
+void fp8_quantize_act(const Tensor& x, Tensor& x8, const Tensor& inv_scale, const OptTensor& amax_cur) {
+  chk_bf16(x, "x"); chk_2d_rowmajor(x, "x");
+  TORCH_CHECK(x8.is_cuda() && x8.element_size() == 1 && x8.dim() == 2 && x8.stride(1) == 1 && x8.sizes() == x.sizes(), "x8: one-byte tensor shaped like x");
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::fp8_quantize_act(x.data_ptr(), x.stride(0), x8.data_ptr(), x8.stride(0), (int)x.size(0), (int)x.size(1), f32ptr(inv_scale),
+                       const_cast<float*>(f32ptr(amax_cur)), cur_stream());
+}
+void fp8_prep(Tensor& state, const Tensor& w_scale, Tensor& inv_sx, Tensor& alpha_main, Tensor& alpha_inv, double margin) {
+  const int n = (int)w_scale.numel();
+  TORCH_CHECK(state.numel() == 2 * n && inv_sx.numel() == n && alpha_main.numel() == n && alpha_inv.numel() == n, "fp8_prep: size mismatch");
+  TORCH_CHECK(state.is_contiguous() && w_scale.is_contiguous() && inv_sx.is_contiguous() && alpha_main.is_contiguous() && alpha_inv.is_contiguous());
+  c10::cuda::CUDAGuard guard(state.device());
+  rb::fp8_prep(const_cast<float*>(f32ptr(state)), f32ptr(w_scale), const_cast<float*>(f32ptr(inv_sx)), const_cast<float*>(f32ptr(alpha_main)),
+               const_cast<float*>(f32ptr(alpha_inv)), n, (float)margin, cur_stream());
 }
 
 // out[M,N] = dy[M,Kb]·W[Kb,N] + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)     (fused input gradient of a stacked LoRA group)
@@ -436,6 +473,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
   m.def("dropout_expand", &dropout_expand);
   m.def("dropout_combine", &dropout_combine);
+  m.def("fp8_quantize_weight", &fp8_quantize_weight);
+  m.def("fp8_quantize_act", &fp8_quantize_act, py::arg("x"), py::arg("x8"), py::arg("inv_scale"), py::arg("amax_cur") = py::none());
+  m.def("fp8_prep", &fp8_prep);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_set_trace", [](const OptTensor& t) {
     if (!t.has_value()) { rb::attention_set_trace(nullptr); return; }

@@ -39,6 +39,8 @@ struct GemmDesc {
   long long ldr = 0;
   const void* bias = nullptr;      // bf16 [N], added in fp32 (after alpha, before the residual)
   float alpha = 1.0f;
+  const float* alpha_dev = nullptr;  // optional device scalar multiplied into alpha
+  bool fp8 = false;  // A1 / B1 hold E4M3 bytes (K-major, leading dimensions in bytes); A2 / B2 (the LoRA branch) stay bf16
   int block_n = 0;  // 0 = auto, else 128 or 256
   int split_k = 1;  // 1 = off, 0 = auto, >1 = fixed (fp32 accumulate outputs only: partial sums via atomics)
   int cta_pair = -1; // -1 = auto, 0 = single-CTA tiles, 1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles; needs block_n 256)

@@ -53,6 +53,8 @@ struct KernelArgs {
   long long ldr;
   const bf16* bias;  // [N], added in fp32 (Pythia projections carry biases)
   float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha (fp8 dequantisation scales live on the device)
+  int fp8;                 // segment 1 (A1, B1) holds E4M3 bytes: k-blocks of 128 elements, kind::f8f6f4 MMAs
   int out_f32, accumulate;
   int num_m_tiles, num_n_tiles;
   int tiles_per_group;  // N-tiles per output-column group (the last one of a group may be ragged)
@@ -185,7 +187,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_work = num_tiles * p.split_k;
-  const int kb1 = (p.K1 + BLOCK_K - 1) / BLOCK_K;
+  const int kstep1 = p.fp8 ? 2 * BLOCK_K : BLOCK_K;  // elements per k-block of segment 1 (always 128 bytes per row)
+  const int kb1 = (p.K1 + kstep1 - 1) / kstep1;
   const int kb2 = (p.K2 + BLOCK_K - 1) / BLOCK_K;
   const int num_kb = kb1 + kb2;
   const int kb_per_split = (num_kb + p.split_k - 1) / p.split_k;
@@ -218,8 +221,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           const uint32_t fb = full_addr0 + stage * 8;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * L::kStageBytes);  // both CTAs' bytes land here
           if (kb < kb1) {
-            load_operand<BLOCK_M, A_MN, PAIR>(&map_a1, fb, sa, m0, a1_k + kb * BLOCK_K, kEvictNormal);
-            load_operand<L::kBRows, B_MN, PAIR>(&map_b1, fb, sb, b1_n + b_half, b1_k + kb * BLOCK_K, kEvictLast);
+            load_operand<BLOCK_M, A_MN, PAIR>(&map_a1, fb, sa, m0, a1_k + kb * kstep1, kEvictNormal);
+            load_operand<L::kBRows, B_MN, PAIR>(&map_b1, fb, sb, b1_n + b_half, b1_k + kb * kstep1, kEvictLast);
           } else {
             const int k = (kb - kb1) * BLOCK_K;
             load_operand<BLOCK_M, false, PAIR>(&map_a2, fb, sa, m0, a2_k + k, kEvictNormal);
@@ -237,9 +240,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     if (lane == 0 && leader) {
       constexpr uint32_t idesc1 = make_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t idesc2 = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc8 = make_idesc_e4m3(kTileM, BLOCK_N);
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_flag) {
         if constexpr (PAIR) umma_f16_ss_pair(d, da, db, idesc, acc_flag);
         else umma_f16_ss(d, da, db, idesc, acc_flag);
+      };
+      auto mma8 = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
+        if constexpr (PAIR) umma_f8_ss_pair(d, da, db, idesc8, acc_flag);
+        else umma_f8_ss(d, da, db, idesc8, acc_flag);
       };
       auto commit = [&](uint64_t* bar) {
         if constexpr (PAIR) umma_commit_pair(bar, 3);
@@ -263,7 +271,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
           if (p.trace != nullptr && blockIdx.x == 0 && tr_m < 512) p.trace[1 * 512 + tr_m++] = clock64();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
-          if (kb < kb1) {
+          if (kb < kb1 && p.fp8) {  // E4M3 rows of 128 bytes: four K = 32 steps, same byte offsets as bf16
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma8(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), ((kb - kb_begin) | k) != 0);
+          } else if (kb < kb1) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               mma(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc1, ((kb - kb_begin) | k) != 0);
@@ -300,6 +312,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     const bool res_vec = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const bool out_vec = (p.ldc % (p.out_f32 ? 4 : 8) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const bool lean = p.bias == nullptr && (p.residual == nullptr || p.res_tma);  // epilogue is alpha (+ TMA residual) only
+    const float alpha_eff = p.alpha * (p.alpha_dev != nullptr ? *p.alpha_dev : 1.0f);
     int slab_counter = 0;
     int tr_e = 0;
     // residual slabs travel by TMA into the (swizzled) output slab one slab ahead of their use; each thread then
@@ -368,7 +381,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-                f[i] = __uint_as_float(raw) * p.alpha;
+                f[i] = __uint_as_float(raw) * alpha_eff;
               }
               add_bias8(p.bias, col0 + q * 8, n_lim, f);
               if (p.res_tma) {
@@ -399,7 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-                f[i] = fmaf(__uint_as_float(raw), p.alpha, a[i]);
+                f[i] = fmaf(__uint_as_float(raw), alpha_eff, a[i]);
               }
               packed[q] = pack8(f);
             }
@@ -410,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const uint32_t raw = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-                f[i] = __uint_as_float(raw) * p.alpha;
+                f[i] = __uint_as_float(raw) * alpha_eff;
               }
               packed[q] = pack8(f);
             }
@@ -454,20 +467,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
-              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
-              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
-              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * alpha_eff;
+              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * alpha_eff;
+              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * alpha_eff;
+              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * alpha_eff;
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + q * 4), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
             }
           } else if (p.split_k > 1) {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
-              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
-              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
-              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              const float a0 = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * alpha_eff;
+              const float a1 = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * alpha_eff;
+              const float a2 = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * alpha_eff;
+              const float a3 = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * alpha_eff;
               if (out_vec && col0 + q * 4 + 4 <= n_lim) {  // one 16-byte vector reduction instead of four scalar atomics
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + q * 4), "f"(a0), "f"(a1), "f"(a2), "f"(a3)
                              : "memory");
@@ -484,20 +497,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 float4 o = *reinterpret_cast<const float4*>(op + q * 4);
-                o.x = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]), p.alpha, o.x);
-                o.y = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]), p.alpha, o.y);
-                o.z = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]), p.alpha, o.z);
-                o.w = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]), p.alpha, o.w);
+                o.x = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]), alpha_eff, o.x);
+                o.y = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]), alpha_eff, o.y);
+                o.z = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]), alpha_eff, o.z);
+                o.w = fmaf(__uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]), alpha_eff, o.w);
                 *reinterpret_cast<float4*>(op + q * 4) = o;
               }
             } else {
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 float4 o;
-                o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
-                o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
-                o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
-                o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+                o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * alpha_eff;
+                o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * alpha_eff;
+                o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * alpha_eff;
+                o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * alpha_eff;
                 *reinterpret_cast<float4*>(op + q * 4) = o;
               }
             }
@@ -506,10 +519,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               float4 o;
-              o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * p.alpha;
-              o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * p.alpha;
-              o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * p.alpha;
-              o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * p.alpha;
+              o.x = __uint_as_float(q < 8 ? r0[q * 4 + 0] : r1[(q - 8) * 4 + 0]) * alpha_eff;
+              o.y = __uint_as_float(q < 8 ? r0[q * 4 + 1] : r1[(q - 8) * 4 + 1]) * alpha_eff;
+              o.z = __uint_as_float(q < 8 ? r0[q * 4 + 2] : r1[(q - 8) * 4 + 2]) * alpha_eff;
+              o.w = __uint_as_float(q < 8 ? r0[q * 4 + 3] : r1[(q - 8) * 4 + 3]) * alpha_eff;
               if (out_vec && col0 + q * 4 + 4 <= n_lim) {
                 if (p.accumulate) {
                   const float4 old = *reinterpret_cast<const float4*>(op + q * 4);
@@ -529,7 +542,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
             for (int q = 0; q < 8; ++q) {
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(q < 4 ? r0[q * 8 + i] : r1[(q - 4) * 8 + i]) * p.alpha;
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(q < 4 ? r0[q * 8 + i] : r1[(q - 4) * 8 + i]) * alpha_eff;
               const bool fullv = col0 + q * 8 + 8 <= n_lim;
               add_bias8(p.bias, col0 + q * 8, n_lim, f);
               if (p.residual != nullptr) {
@@ -899,16 +912,16 @@ static PFN_encodeTiled get_encode() {
 struct MapKey {
   const void* ptr;
   long long inner, outer, ld;
-  int box_inner, box_outer;
+  int box_inner, box_outer, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     auto mix = [&](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.esize);
     return h;
   }
 };
@@ -921,21 +934,23 @@ void gemm_clear_descriptor_cache() {
 }
 
 // 2-D bf16 tensor, `inner` contiguous elements per row, `outer` rows `ld` elements apart, 128B swizzle.
-static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer,
+                               int esize = 2) {
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, esize};
   {
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
   }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("gemm operand pointer must be 16-byte aligned");
-  if ((ld * 2) % 16 != 0) throw std::runtime_error("gemm operand leading dimension must be a multiple of 8 elements");
+  if ((ld * esize) % 16 != 0) throw std::runtime_error("gemm operand leading dimension must be a multiple of 16 bytes");
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  const CUtensorMapDataType dt = esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_ERROR_INVALID_CONTEXT) {
@@ -944,7 +959,7 @@ static CUtensorMap make_map_2d(const void* ptr, long long inner, long long outer
     int dev = 0;
     check(cudaGetDevice(&dev), "cudaGetDevice");
     check(cudaSetDevice(dev), "cudaSetDevice");
-    r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -982,7 +997,8 @@ CUtensorMap make_map_3d_bf16(const void* ptr, long long d0, long long d1, long l
 }
 
 // Operand covering `mn` rows/cols of the output dimension and `k` of the reduction dimension.
-static CUtensorMap operand_map(const Operand& o, long long mn, long long k, int block_mn) {
+static CUtensorMap operand_map(const Operand& o, long long mn, long long k, int block_mn, bool fp8 = false) {
+  if (fp8) return make_map_2d(o.ptr, k, mn, o.ld, 2 * BLOCK_K, block_mn, 1);  // E4M3 bytes, K-major only
   if (!o.mn_major) return make_map_2d(o.ptr, k, mn, o.ld, BLOCK_K, block_mn);
   return make_map_2d(o.ptr, mn, k, o.ld, 64, BLOCK_K);
 }
@@ -1000,7 +1016,7 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   p.out = d.out; p.ldc = d.ldc; p.residual = reinterpret_cast<const bf16*>(d.residual); p.ldr = d.ldr;
   p.bias = reinterpret_cast<const bf16*>(d.bias);
   if (d.bias != nullptr && d.out_f32) throw std::runtime_error("gemm: bias is only fused for bf16 outputs");
-  p.alpha = d.alpha; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
+  p.alpha = d.alpha; p.alpha_dev = d.alpha_dev; p.fp8 = d.fp8 ? 1 : 0; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
   p.num_m_tiles = ceil_div(d.M, kTileM);
   const int groups = ceil_div(d.N, p.n_per_group);
   // tiles never straddle a group: the last tile of a group may be ragged (its tail columns are computed but not
@@ -1011,12 +1027,13 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
 
   // K extents of the global tensors include the per-group windows
   const long long a1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.a1_group_kofs;
-  CUtensorMap ma1 = operand_map(d.a1, d.M, a1_k_total, BLOCK_M);
+  if (d.fp8 && (A_MN || B_MN)) throw std::runtime_error("gemm: fp8 operands must be K-major");
+  CUtensorMap ma1 = operand_map(d.a1, d.M, a1_k_total, BLOCK_M, d.fp8);
   const int mgroups = d.m_per_group > 0 ? ceil_div(d.M, d.m_per_group) : 1;
   const long long b1_mn_total = (d.b1_local_n ? (long long)p.n_per_group : (long long)d.N) + (long long)(mgroups - 1) * d.b1_mn_ofs_per_mgroup;
   const long long b1_k_total = (long long)d.K1 + (long long)(groups - 1) * d.b1_group_kofs;
   if (d.m_per_group > 0 && (d.m_per_group % kTileM) != 0) throw std::runtime_error("gemm: m_per_group must be a multiple of the M tile");
-  CUtensorMap mb1 = operand_map(d.b1, b1_mn_total, b1_k_total, L::kBRows);
+  CUtensorMap mb1 = operand_map(d.b1, b1_mn_total, b1_k_total, L::kBRows, d.fp8);
   CUtensorMap ma2 = ma1, mb2 = mb1;
   if (d.K2 > 0) {
     if (d.a2.mn_major || d.b2.mn_major) throw std::runtime_error("gemm: the LoRA (A2/B2) operands must be K-major");
@@ -1031,7 +1048,7 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = ceil_div(d.K1, BLOCK_K) + ceil_div(d.K2, BLOCK_K);
+  const int num_kb = ceil_div(d.K1, d.fp8 ? 2 * BLOCK_K : BLOCK_K) + ceil_div(d.K2, BLOCK_K);
   int split = d.split_k;
   if (split == 0) {  // auto: fill the machine when there are few output tiles and a long reduction
     split = 1;

@@ -83,4 +83,15 @@ void threshold_prune(void* x, bool is_f32, long long n, const float* thr, cudaSt
 void magnitude_quantile(const void* x, bool is_f32, long long n, float ratio, float* thr, void* workspace, cudaStream_t s);
 size_t magnitude_quantile_workspace_bytes();
 
+// ---- fp8 (E4M3) quantisation for the frozen-weight tensor-core path (fp8.cu) ---------------------------
+// weights: amax -> scale -> quantise (scale / inv_scale are device scalars)
+void fp8_quantize_weight(const void* w, long long ld, void* w8, long long ld8, int R, int C, float* amax_scratch, float* scale,
+                         float* inv_scale, cudaStream_t s);
+// activations: x8 = sat_e4m3(x * *inv_scale); |x| amax recorded into *amax_cur (may be null)
+void fp8_quantize_act(const void* x, long long ld, void* x8, long long ld8, int R, int C, const float* inv_scale, float* amax_cur,
+                      cudaStream_t s);
+// once per micro-step: rotate the per-site amax state and derive 1/s_x, s_x*s_w and 1/(s_x*s_w)
+void fp8_prep(float* state, const float* w_scale, float* inv_sx, float* alpha_main, float* alpha_inv, int n, float margin,
+              cudaStream_t s);
+
 }  // namespace rb

@@ -282,6 +282,26 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4: 8-bit float operands (E4M3 here), K = 32 per instruction, fp32 accumulate (may be mixed with kind::f16
+// instructions on the same accumulator: both produce fp32 partial sums)
+__device__ __forceinline__ void umma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once all prior MMAs of this thread completed) on the barrier at this shared-memory offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -298,6 +318,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask = 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// kind::f8f6f4 with E4M3 A / B (format code 0), K-major operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), 128-byte swizzle:

@@ -78,7 +78,7 @@ class FusedLlamaStepper:
     def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
                  transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096,
-                 overlap_wgrad: bool = True, attention: str = "auto"):
+                 overlap_wgrad: bool = True, attention: str = "auto", fp8: bool = False):
         ok, why = supports(model)
         if not ok:
             raise RuntimeError(why)
@@ -240,6 +240,19 @@ class FusedLlamaStepper:
         self._replays = 0
         self._launches_per_micro = 0
         self._attn_saved: List = []
+        # ---- fp8 frozen-weight path: E4M3 copies of the stacked weights + per-site activation scales (csrc/fp8.cu)
+        self.fp8 = bool(fp8) or os.environ.get("RELORA_B200_FP8", "0") == "1"
+        if self.fp8:
+            u8 = lambda *sh: torch.zeros(*sh, dtype=torch.uint8, device=dev)  # noqa: E731
+            self.W8 = [u8(L, 3 * h, h), u8(L, h, h), u8(L, 2 * fp, h), u8(L, h, fp)]  # sites: qkv, o, gate/up, down
+            f32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)  # noqa: E731
+            self.w_scale, self.w_inv_scale, self._amax_scratch = f32(L, 4), f32(L, 4), f32(1)
+            self.act_state = f32(L, 4, 2)  # [amax of the previous micro-step, amax being recorded]
+            self.inv_sx, self.alpha_main, self.alpha_inv = f32(L, 4), f32(L, 4), f32(L, 4)
+            self.fp8_margin = float(os.environ.get("RELORA_B200_FP8_MARGIN", "1.5"))
+            self._fp8_calibrated = False
+            self._quantize_weights()
+        self._fp8_calibrating = False
         attention = os.environ.get("RELORA_B200_ATTENTION", attention)
         native_ok = self.hd % 8 == 0 and self.hd <= 64
         if attention == "native" and not native_ok:
@@ -258,6 +271,15 @@ class FusedLlamaStepper:
     def _rehome(param: torch.nn.Parameter, dst: torch.Tensor):
         dst.copy_(param.data)
         param.data = dst
+
+    @torch.no_grad()
+    def _quantize_weights(self):
+        """(Re)build the E4M3 copies of the frozen weights and their per-tensor scales (at start-up and after every merge)."""
+        stacks = (self.Wqkv, self.Wo, self.Wgu, self.Wd)
+        for l in range(self.L):
+            for s_i in range(4):
+                self.C.fp8_quantize_weight(stacks[s_i][l], self.W8[s_i][l], self._amax_scratch, self.w_scale[l, s_i:s_i + 1],
+                                           self.w_inv_scale[l, s_i:s_i + 1])
 
     def _alloc(self, B: int, T: int):
         dev, h, f, r, L = self.device, self.h, self.fp, self.r, self.L  # f: padded intermediate size
@@ -293,6 +315,9 @@ class FusedLlamaStepper:
         self.dgu = e(M, 2 * f)
         self.dhmid, self.dhmid2 = e(M, f), e(M, f)
         self.du_bufs = {"d": e(M, r), "gu": e(M, 2 * r), "o": e(M, r), "qkv": e(M, 3 * r)}
+        if self.fp8:
+            self.x8_h = torch.empty(M, h, dtype=torch.uint8, device=dev)
+            self.x8_f = torch.empty(M, f, dtype=torch.uint8, device=dev)
         if self.native_attn:
             self.attn_o = e(L, M, h)
             self.lse = torch.empty(L, B, self.nh, T, dtype=torch.float32, device=dev)
@@ -325,10 +350,24 @@ class FusedLlamaStepper:
             o = F_.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=True)
         return o.detach().transpose(1, 2).reshape(self.M_, self.h)
 
-    def _lora_group_fwd(self, xn, xd, A, B, W, u, out, *, G, K, Ng, residual=None):
-        """u = s·xd_g·A_gᵀ (grouped) ; out = [xn | u]·[W | B]ᵀ (+ residual)."""
+    def _lora_group_fwd(self, xn, xd, A, B, W, u, out, *, G, K, Ng, residual=None, site=None):
+        """u = s·xd_g·A_gᵀ (grouped) ; out = [xn | u]·[W | B]ᵀ (+ residual).
+
+        fp8 path (``site = (layer, index)``): xn is quantised to E4M3 with the site's delayed scale and multiplied with the E4M3
+        copy of W on the kind::f8f6f4 tensor-core path; the bf16 LoRA term shares the accumulator, so u is produced pre-divided
+        by the product scale s_x·s_w, which the epilogue multiplies back."""
         g, r, M = fused.gemm, self.r, self.M_
         drop = self.p > 0 and xd.shape[1] == G * K
+        if self.fp8 and site is not None:
+            l, s_i = site
+            x8 = self.x8_h if K == self.h else self.x8_f
+            self.C.fp8_quantize_act(xn, x8, self.inv_sx[l, s_i:s_i + 1], self.act_state[l, s_i, 1:2])
+        if self.fp8 and site is not None and not self._fp8_calibrating:
+            g(xd, A, u, M=M, N=G * r, K1=K, n_per_group=r, a1_group_kofs=K if drop else 0, alpha=self.scale,
+              alpha_dev=self.alpha_inv[l, s_i:s_i + 1])
+            g(x8, self.W8[s_i][l], out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=residual,
+              fp8=True, alpha_dev=self.alpha_main[l, s_i:s_i + 1])
+            return
         g(xd, A, u, M=M, N=G * r, K1=K, n_per_group=r, a1_group_kofs=K if drop else 0, alpha=self.scale)
         g(xn, W, out, M=M, N=G * Ng, K1=K, a2=u, b2=B, K2=r, n_per_group=Ng, a2_group_kofs=r, residual=residual)
 
@@ -354,7 +393,7 @@ class FusedLlamaStepper:
                 xn = xn if xn.is_contiguous() else self.xn
                 C.rmsnorm_fwd(x, S.w1, xn, self.rstd1[sl], self.eps, None, None, [], 0.0)
                 xd = xn
-            self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h)
+            self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h, site=(l, 0))
             C.rope_inplace(qkv, self.T_, 2 * self.nh, self.hd, self.hd, self.cos, self.sin, False, 0)
             attn = self._attention(qkv, train, sl)
             if p > 0:
@@ -364,7 +403,7 @@ class FusedLlamaStepper:
                 xd_o = attn
                 if train:
                     self.xd_o[sl].copy_(attn)
-            self._lora_group_fwd(attn, xd_o, S.A_o, S.B_o, S.Wo, self.u_o[sl], x1, G=1, K=h, Ng=h, residual=x)
+            self._lora_group_fwd(attn, xd_o, S.A_o, S.B_o, S.Wo, self.u_o[sl], x1, G=1, K=h, Ng=h, residual=x, site=(l, 1))
             # ---- MLP block
             if p > 0:
                 xd = self.xd_gu[sl]
@@ -374,7 +413,7 @@ class FusedLlamaStepper:
                 xn = self.xd_gu[sl] if self.p == 0 else self.xn
                 C.rmsnorm_fwd(x1, S.w2, xn, self.rstd2[sl], self.eps, None, None, [], 0.0)
                 xd = xn
-            self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f)
+            self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f, site=(l, 2))
             if p > 0:
                 xd_d = self.xd_d[sl]
                 C.swiglu_fwd(gu, self.hmid, xd_d, seed, S.key_d, p)  # activation + its dropout-expanded copy in one pass
@@ -383,7 +422,7 @@ class FusedLlamaStepper:
                 xd_d = self.hmid
                 if train:
                     self.xd_d[sl].copy_(self.hmid)
-            self._lora_group_fwd(self.hmid, xd_d, S.A_d, S.B_d, S.Wd, self.u_d[sl], x_next, G=1, K=f, Ng=h, residual=x1)
+            self._lora_group_fwd(self.hmid, xd_d, S.A_d, S.B_d, S.Wd, self.u_d[sl], x_next, G=1, K=f, Ng=h, residual=x1, site=(l, 3))
         x_last = self.x_in[self.L] if train else self.x_in[self.L % 2]
         C.rmsnorm_fwd(x_last, self.w_norm, self.xf, self.rstd_f, self.eps, None, None, [], 0.0)
         return x_last
@@ -406,7 +445,7 @@ class FusedLlamaStepper:
                 g(lg, hc, self.gW_head, M=V, N=h, K1=m, a1_mn=True, b1_mn=True, accumulate=True)
         torch.div(self.loss_sum[0], float(n_valid), out=self.loss_out)
 
-    def _lora_group_bwd(self, dy, S_B, S_W, S_A, gA, gB, xd, u, keys, *, G, K, Ng, base_out, out, tag):
+    def _lora_group_bwd(self, dy, S_B, S_W, S_A, gA, gB, xd, u, keys, *, G, K, Ng, base_out, out, tag, site=None):
         """Backward of one stacked LoRA group.  dy [M, G·Ng] -> out [M, K] (grad of the group's input).
 
         The two weight-gradient GEMMs only read (dy, du, xd, u), so they are forked onto a side stream and fill the
@@ -423,8 +462,10 @@ class FusedLlamaStepper:
         def wgrads():  # fp32, accumulated across micro-batches, split-K over tokens
             g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
               m_per_group=r if G > 1 else 0, b1_mn_ofs_per_mgroup=0 if shared_x else K)
+            # fp8 path: the saved u is u / (s_x·s_w); the product scale is multiplied back here
             g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
-              m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0)
+              m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0,
+              alpha_dev=self.alpha_main[site[0], site[1]:site[1] + 1] if (self.fp8 and site is not None) else None)
 
         if self.side is not None:
             fork = torch.cuda.Event()
@@ -475,17 +516,17 @@ class FusedLlamaStepper:
             S = self.layers[l]
             # ---- MLP: x_next = hmid·Wdᵀ + u_d·B_dᵀ + x1
             self._lora_group_bwd(dx, S.B_d, S.Wd, S.A_d, S.gA_d, S.gB_d, self.xd_d[l], self.u_d[l], [S.key_d],
-                                 G=1, K=f, Ng=h, base_out=self.dhmid, out=self.dhmid2, tag="d")
+                                 G=1, K=f, Ng=h, base_out=self.dhmid, out=self.dhmid2, tag="d", site=(l, 3))
             self._join("gu")  # the previous layer's gate/up weight gradients read dgu / du_gu
             C.swiglu_bwd(self.dhmid2, self.gu[l], self.dgu)
             self._lora_group_bwd(self.dgu, S.B_gu, S.Wgu, S.A_gu, S.gA_gu, S.gB_gu, self.xd_gu[l], self.u_gu[l], S.keys_gu,
-                                 G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2, tag="gu")
+                                 G=2, K=h, Ng=f, base_out=self.dxn, out=self.dxn2, tag="gu", site=(l, 2))
             self._join("o")  # ... and its o_proj weight gradients read the buffer this norm backward writes
             C.rmsnorm_bwd(self.dxn2, self.x1[l], S.w2, self.rstd2[l], dx, dx_other, S.gw2, ws, tk)
             dx, dx_other = dx_other, dx  # dx = grad wrt x1
             # ---- attention: x1 = attn·Woᵀ + u_o·B_oᵀ + x
             self._lora_group_bwd(dx, S.B_o, S.Wo, S.A_o, S.gA_o, S.gB_o, self.xd_o[l], self.u_o[l], [S.key_o],
-                                 G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn, tag="o")
+                                 G=1, K=h, Ng=h, base_out=self.dxn, out=self.dattn, tag="o", site=(l, 1))
             if self.native_attn:
                 self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
                 C.attention_bwd(self.qkv[l], self.attn_o[l], self.dattn, self.lse[l], self.delta, self.dqkv, B, T, nh, hd,
@@ -505,7 +546,7 @@ class FusedLlamaStepper:
                 d5[:, :, 0].copy_(dq.transpose(1, 2)); d5[:, :, 1].copy_(dk.transpose(1, 2)); d5[:, :, 2].copy_(dv.transpose(1, 2))
                 C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)
             self._lora_group_bwd(self.dqkv, S.B_qkv, S.Wqkv, S.A_qkv, S.gA_qkv, S.gB_qkv, self.xd_qkv[l], self.u_qkv[l],
-                                 S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2, tag="qkv")
+                                 S.keys_qkv, G=3, K=h, Ng=h, base_out=self.dxn, out=self.dxn2, tag="qkv", site=(l, 0))
             self._join("d")  # this layer's down_proj weight gradients read the buffer written next
             C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1, ws, tk)
             dx, dx_other = dx_other, dx
@@ -514,9 +555,22 @@ class FusedLlamaStepper:
             self._join(tag)
         self._attn_saved.clear()
 
+    def _fp8_calibrate(self):
+        """Bootstrap of the delayed activation scales: one bf16 forward that only *records* every site's amax.  (Starting the
+        fp8 path cold would saturate the first sites, shrink everything downstream and need one pass per site to recover.)"""
+        self._fp8_calibrating = True
+        try:
+            self.labels.view(self.B_, self.T_)[:, :-1].copy_(self.ids[:, 1:])
+            self._forward(True)
+        finally:
+            self._fp8_calibrating = False
+        self._fp8_calibrated = True
+
     def _micro_body(self):
         self.labels.view(self.B_, self.T_)[:, :-1].copy_(self.ids[:, 1:])
         self.labels.view(self.B_, self.T_)[:, -1].fill_(-100)
+        if self.fp8:  # rotate the activation amax state, derive this micro-step's scales
+            self.C.fp8_prep(self.act_state, self.w_scale, self.inv_sx, self.alpha_main, self.alpha_inv, self.fp8_margin)
         self._forward(True)
         self._loss_and_head_backward(True)
         self._backward()
@@ -530,6 +584,8 @@ class FusedLlamaStepper:
             self._alloc(B, T)
             self._graph = None
         self.ids.copy_(input_ids, non_blocking=True)
+        if self.fp8 and not self._fp8_calibrated:
+            self._fp8_calibrate()
         if not self.use_graphs:
             self._micro_body()
             return self.loss_out.clone()
@@ -631,6 +687,8 @@ class FusedLlamaStepper:
                 self.C.fill_uniform_hash(m.lora_A.weight.data, sd, 1.0 / math.sqrt(m.in_features))
                 m.lora_B.weight.data.zero_()
         self.model.n_restarts += 1
+        if self.fp8:
+            self._quantize_weights()
 
     def launches_in_window(self, n_steps: int) -> int:
         """Kernel launches of this extension since ``reset_launch_count`` (graph replays included)."""

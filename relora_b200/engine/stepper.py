@@ -126,7 +126,8 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
         ok, why = supports(model, args)
         if ok:
             return FusedLlamaStepper(model, info, cuda_graphs=getattr(args, "cuda_graphs", True),
-                                     attention=getattr(args, "attention", "auto"), **kw)
+                                     attention=getattr(args, "attention", "auto"),
+                                     fp8=getattr(args, "frozen_dtype", None) == "fp8", **kw)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
     kw["transport"] = "nccl"  # the module path reduces through the process group (NCCL / gloo)

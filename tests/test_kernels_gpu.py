@@ -563,3 +563,38 @@ def test_attention_fwd_bwd(C, B, T, nh, hd):
     for i, (name, ref_t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
         e = _relerr(d5[:, :, i].transpose(1, 2), ref_t.grad)
         assert e < 2e-2, (name, e)
+
+
+# ----------------------------------------------------------------------------------------- fp8 frozen-weight path
+@pytest.mark.parametrize("M,N,K,pair", [(256, 256, 256, 0), (1000, 768, 640, 0), (512, 1024, 2048, 1), (12288, 2304, 768, 0)])
+def test_gemm_fp8_frozen_path_with_bf16_lora_branch(C, F, M, N, K, pair):
+    """x·Wᵀ on the E4M3 tensor-core path (tcgen05 kind::f8f6f4, per-tensor scales) with the bf16 LoRA branch accumulated into
+    the same tensor-memory accumulator; checked against an fp32 product of the *dequantised* operands."""
+    torch.manual_seed(K + N)
+    r = 128
+    x, W = _rand(M, K), _rand(N, K, scale=0.05)
+    u, B = _rand(M, r), _rand(N, r, scale=0.05)
+    res = _rand(M, N)
+    f32 = lambda v: torch.tensor([v], dtype=torch.float32, device="cuda")  # noqa: E731
+    scratch, sw, inv_sw = f32(0.0), f32(0.0), f32(0.0)
+    W8 = torch.empty(N, K, dtype=torch.uint8, device="cuda")
+    C.fp8_quantize_weight(W, W8, scratch, sw, inv_sw)
+    assert abs(float(sw) - float(W.float().abs().max()) / 448.0) < 1e-6
+    sx = float(x.float().abs().max()) / 448.0
+    x8 = torch.empty(M, K, dtype=torch.uint8, device="cuda")
+    amax = f32(0.0)
+    C.fp8_quantize_act(x, x8, f32(1.0 / sx), amax)
+    assert abs(float(amax) - float(x.float().abs().max())) < 1e-6
+    xq = x8.view(torch.float8_e4m3fn).float() * sx
+    Wq = W8.view(torch.float8_e4m3fn).float() * float(sw)
+    assert _relerr(xq, x) < 0.05 and _relerr(Wq, W) < 0.05  # E4M3: 3 mantissa bits
+    alpha = sx * float(sw)
+    u_scaled = (u.float() / alpha).to(BF)  # the LoRA term shares the accumulator, so it is pre-divided by the product scale
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    F.gemm(x8, W8, out, M=M, N=N, K1=K, a2=u_scaled, b2=B, K2=r, residual=res, fp8=True, alpha_dev=f32(alpha),
+           block_n=256 if pair else 0, pair=pair)
+    want = xq @ Wq.t() + (u_scaled.float() * alpha) @ B.float().t() + res.float()
+    assert _relerr(out, want) < 6e-3
+    # and it is close to the unquantised product (quantisation noise only)
+    full = x.float() @ W.float().t() + u.float() @ B.float().t() + res.float()
+    assert _relerr(out, full) < 0.06
