@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int qb = gridDim.x - 1 - blockIdx.x;  // long (late) query blocks first
   const int head = blockIdx.y, b = blockIdx.z;
   const int t0 = qb * BQ;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
 // delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ld_o, const bf16* __restrict__ dout,
                                                          long long ld_do, float* __restrict__ delta, int B, int T, int nh, int hd) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)B * T * nh;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int h = int(i % nh);
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int qb = gridDim.x - 1 - blockIdx.x;
   const int head = blockIdx.y, b = blockIdx.z;
   const int t0 = qb * BQ;
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -461,6 +467,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int kb = blockIdx.x;  // early key blocks see the most queries and are scheduled first
   const int head = blockIdx.y, b = blockIdx.z;
   const int kstart = kb * BQ;
@@ -488,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -670,7 +678,7 @@ void attention_fwd(const AttnDesc& d, cudaStream_t stream) {
   p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
-  attn_fwd_kernel<<<grid, kThreads, kFwdSmem, stream>>>(map, p);
+  launch_k(attn_fwd_kernel, grid, kThreads, kFwdSmem, stream, map, p);
   RB_CHECK_LAUNCH("attn_fwd_kernel");
 }
 
@@ -688,7 +696,7 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
   {
     const long long total = rows * d.nh;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-    attn_delta_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d.out), d.ld_out, reinterpret_cast<const bf16*>(d.dout),
+    launch_k(attn_delta_kernel, grid, 256, 0, stream, reinterpret_cast<const bf16*>(d.out), d.ld_out, reinterpret_cast<const bf16*>(d.dout),
                                                 d.ld_dout, d.delta, d.B, d.T, d.nh, d.hd);
     RB_CHECK_LAUNCH("attn_delta_kernel");
   }
@@ -697,9 +705,9 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
   p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
   p.scale = d.scale; p.scale_log2 = d.scale * 1.4426950408889634f;
   dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
-  attn_bwd_dkv_kernel<<<grid, kThreads, kDkvSmem, stream>>>(map_qkv, map_do, p);
+  launch_k(attn_bwd_dkv_kernel, grid, kThreads, kDkvSmem, stream, map_qkv, map_do, p);
   RB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-  attn_bwd_dq_kernel<<<grid, kThreads, kDqSmem, stream>>>(map_qkv, map_do, p);
+  launch_k(attn_bwd_dq_kernel, grid, kThreads, kDqSmem, stream, map_qkv, map_do, p);
   RB_CHECK_LAUNCH("attn_bwd_dq_kernel");
 }
 

@@ -48,6 +48,17 @@ rb::Operand operand(const Tensor& t, bool mn_major, const char* name) {
   return o;
 }
 
+rb::Fp8Out fp8_out(const OptTensor& q8, const OptTensor& inv_scale, const OptTensor& amax, int64_t rows, int64_t cols) {
+  rb::Fp8Out f;
+  if (!q8.has_value()) return f;
+  TORCH_CHECK(q8->is_cuda() && q8->element_size() == 1 && q8->dim() == 2 && q8->stride(1) == 1 && q8->size(0) == rows && q8->size(1) == cols,
+              "fp8 output: one-byte [rows, cols] tensor");
+  TORCH_CHECK(inv_scale.has_value() && amax.has_value(), "fp8 output needs inv_scale and amax");
+  f.q = reinterpret_cast<uint8_t*>(q8->data_ptr()); f.ld = q8->stride(0);
+  f.inv_scale = f32ptr(inv_scale); f.amax = const_cast<float*>(f32ptr(amax));
+  return f;
+}
+
 // out[M,N] = alpha*(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
@@ -99,7 +110,7 @@ void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N,
 }
 
 void rmsnorm_fwd(const Tensor& x, const Tensor& w, Tensor& y, Tensor& rstd, double eps, const OptTensor& xd, const OptTensor& seed,
-                 std::vector<int64_t> keys, double p) {
+                 std::vector<int64_t> keys, double p, const OptTensor& q8, const OptTensor& q_inv_scale, const OptTensor& q_amax) {
   chk_bf16(x, "x"); chk_bf16(w, "w"); chk_bf16(y, "y");
   TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && w.is_contiguous(), "rmsnorm: contiguous tensors required");
   const int H = (int)x.size(-1);
@@ -118,7 +129,7 @@ void rmsnorm_fwd(const Tensor& x, const Tensor& w, Tensor& y, Tensor& rstd, doub
   }
   const uint32_t thr = (uint32_t)llround(p * 65536.0);
   rb::rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), M, H, (float)eps, xdp, G, u32ptr(seed), k, thr,
-                  (float)(1.0 / (1.0 - p)), cur_stream());
+                  (float)(1.0 / (1.0 - p)), fp8_out(q8, q_inv_scale, q_amax, M, H), cur_stream());
 }
 
 void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tensor& rstd, const OptTensor& dx_add, Tensor& dx, Tensor& dw,
@@ -143,7 +154,8 @@ void rmsnorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& w, const Tenso
                   wsp, tk, cur_stream());
 }
 
-void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vector<int64_t> keys, double p) {
+void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vector<int64_t> keys, double p, const OptTensor& q8,
+                    const OptTensor& q_inv_scale, const OptTensor& q_amax) {
   chk_bf16(x, "x"); chk_bf16(xd, "xd");
   TORCH_CHECK(x.is_contiguous() && xd.is_contiguous());
   const int H = (int)x.size(-1);
@@ -154,7 +166,7 @@ void dropout_expand(const Tensor& x, Tensor& xd, const OptTensor& seed, std::vec
   for (int i = 0; i < G && i < 4; ++i) k[i] = (uint32_t)keys[i];
   c10::cuda::CUDAGuard guard(x.device());
   rb::dropout_expand(x.data_ptr(), xd.data_ptr(), M, H, G, u32ptr(seed), k, (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)),
-                     cur_stream());
+                     fp8_out(q8, q_inv_scale, q_amax, M, H), cur_stream());
 }
 
 void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, const OptTensor& seed, std::vector<int64_t> keys, double p) {
@@ -294,7 +306,8 @@ void rope_pack_bwd(const Tensor& dq, const Tensor& dk, const Tensor& dv, Tensor&
                     hd, (int)rotary_dim, cos.data_ptr(), sin.data_ptr(), (int)pos0, cur_stream());
 }
 
-void swiglu_fwd(const Tensor& gu, Tensor& h, const OptTensor& hd, const OptTensor& seed, int64_t key, double p) {
+void swiglu_fwd(const Tensor& gu, Tensor& h, const OptTensor& hd, const OptTensor& seed, int64_t key, double p, const OptTensor& q8,
+                const OptTensor& q_inv_scale, const OptTensor& q_amax) {
   chk_bf16(gu, "gu"); chk_bf16(h, "h"); chk_2d_rowmajor(gu, "gu"); chk_2d_rowmajor(h, "h");
   const int F = (int)h.size(1);
   TORCH_CHECK(gu.size(1) == 2 * F && gu.size(0) == h.size(0));
@@ -307,7 +320,7 @@ void swiglu_fwd(const Tensor& gu, Tensor& h, const OptTensor& hd, const OptTenso
   }
   c10::cuda::CUDAGuard guard(gu.device());
   rb::swiglu_fwd(gu.data_ptr(), gu.stride(0), h.data_ptr(), h.stride(0), (int)h.size(0), F, hdp, ldhd, u32ptr(seed), (uint32_t)key,
-                 (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), cur_stream());
+                 (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), fp8_out(q8, q_inv_scale, q_amax, h.size(0), F), cur_stream());
 }
 void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
   chk_bf16(dh, "dh"); chk_bf16(gu, "gu"); chk_bf16(dgu, "dgu");
@@ -468,10 +481,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 12 * 512, "trace buffer: int64 CUDA tensor of >= 6144 elements");
     rb::gemm_set_trace(t->data_ptr());
   });
-  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_fwd", &rmsnorm_fwd, py::arg("x"), py::arg("w"), py::arg("y"), py::arg("rstd"), py::arg("eps"), py::arg("xd"), py::arg("seed"),
+        py::arg("keys"), py::arg("p"), py::arg("q8") = py::none(), py::arg("q_inv_scale") = py::none(), py::arg("q_amax") = py::none());
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("rmsnorm_bwd_ws_blocks", &rb::rmsnorm_bwd_ws_blocks);
-  m.def("dropout_expand", &dropout_expand);
+  m.def("dropout_expand", &dropout_expand, py::arg("x"), py::arg("xd"), py::arg("seed"), py::arg("keys"), py::arg("p"), py::arg("q8") = py::none(),
+        py::arg("q_inv_scale") = py::none(), py::arg("q_amax") = py::none());
   m.def("dropout_combine", &dropout_combine);
   m.def("fp8_quantize_weight", &fp8_quantize_weight);
   m.def("fp8_quantize_act", &fp8_quantize_act, py::arg("x"), py::arg("x8"), py::arg("inv_scale"), py::arg("amax_cur") = py::none());
@@ -488,7 +503,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rope_inplace", &rope_inplace);
   m.def("rope_pack_bwd", &rope_pack_bwd);
   m.def("swiglu_fwd", &swiglu_fwd, py::arg("gu"), py::arg("h"), py::arg("hd") = py::none(), py::arg("seed") = py::none(),
-        py::arg("key") = 0, py::arg("p") = 0.0);
+        py::arg("key") = 0, py::arg("p") = 0.0, py::arg("q8") = py::none(), py::arg("q_inv_scale") = py::none(), py::arg("q_amax") = py::none());
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd", &embedding_bwd);

@@ -29,7 +29,7 @@ TARGET = os.path.join(PKG, "_C.so")
 
 CUDA_SOURCES = ["gemm_tcgen05.cu", "elementwise.cu", "norm_warp.cu", "rope.cu", "optim.cu", "loss.cu", "attention.cu", "fp8.cu", "comm.cu"]
 CPP_SOURCES = ["bindings.cpp"]
-HEADERS = ["common.cuh", "sm100.cuh", "gemm.h", "tensormap.h", "kernels.h", "attention.h", "comm.h"]
+HEADERS = ["common.cuh", "sm100.cuh", "gemm.h", "tensormap.h", "fp8out.h", "kernels.h", "attention.h", "comm.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -60,12 +60,13 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict
 }
 
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, cudaStream_t s) {
+                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s) {
   if (H % 8 != 0 || H > 8 * 256 * 4) throw std::runtime_error("rmsnorm: H must be a multiple of 8 and <= 8192");
   if (G > 4) throw std::runtime_error("rmsnorm: at most 4 dropout groups");
   uint4 k = make_uint4(0, 0, 0, 0);
   if (G > 0) k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
-  if (rmsnorm_fwd_warp(x, w, y, rstd, M, H, eps, xd, G, seed_ptr, k, thr16, inv_keep, s)) return;
+  if (rmsnorm_fwd_warp(x, w, y, rstd, M, H, eps, xd, G, seed_ptr, k, thr16, inv_keep, f8, s)) return;
+  if (f8.q != nullptr) throw std::runtime_error("rmsnorm: the fused fp8 output needs the warp-per-row kernel (H <= 2048)");
   const int nvec = H / 8;
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)w;
   bf16 *yp = (bf16*)y, *xdp = (bf16*)xd;
@@ -159,7 +160,11 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
 // ============================================================================================ LoRA dropout
 __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restrict__ x, bf16* __restrict__ xd, long long n_vec, int H,
                                                              int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16,
-                                                             float inv_keep) {
+                                                             float inv_keep, Fp8Out f8) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float q_inv = f8.q != nullptr ? *f8.inv_scale : 0.f;
+  float q_max = 0.f;
   const uint32_t base = seed_ptr ? *seed_ptr : 0u;
   const uint32_t seeds[4] = {mix_seed(base, keys.x), mix_seed(base, keys.y), mix_seed(base, keys.z), mix_seed(base, keys.w)};
   const int hv = H / 8;
@@ -178,6 +183,10 @@ __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restr
       const int c = int(i % hv);
       float f[8];
       unpack8(u ? v1 : v0, f);
+      if (f8.q != nullptr) {  // E4M3 copy of the (un-dropped) input for the frozen-weight GEMM
+        *reinterpret_cast<uint2*>(f8.q + row * f8.ld + c * 8) = pack8_e4m3(f, q_inv);
+        q_max = fmaxf(q_max, absmax8(f));
+      }
       for (int g = 0; g < G; ++g) {
         float d[8];
 #pragma unroll
@@ -186,15 +195,16 @@ __global__ void __launch_bounds__(256) dropout_expand_kernel(const bf16* __restr
       }
     }
   }
+  if (f8.q != nullptr) amax_commit(q_max, f8.amax);
 }
 
 void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16,
-                    float inv_keep, cudaStream_t s) {
+                    float inv_keep, Fp8Out f8, cudaStream_t s) {
   if (H % 8 != 0 || G < 1 || G > 4) throw std::runtime_error("dropout_expand: bad shape");
   uint4 k = make_uint4(keys[0], G > 1 ? keys[1] : 0, G > 2 ? keys[2] : 0, G > 3 ? keys[3] : 0);
   const long long n_vec = (long long)M * H / 8;
   const int grid = (int)std::min<long long>((n_vec + 255) / 256, (long long)num_sms() * 8);
-  dropout_expand_kernel<<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)xd, n_vec, H, G, seed_ptr, k, thr16, inv_keep);
+  launch_k(dropout_expand_kernel, grid, 256, 0, s, (const bf16*)x, (bf16*)xd, n_vec, H, G, seed_ptr, k, thr16, inv_keep, f8);
   RB_CHECK_LAUNCH("dropout_expand");
 }
 
@@ -279,7 +289,12 @@ void rope_inplace(void* buf, long long ld, int M, int T, int n_rot_heads, int hd
 // down_proj consumes) so that h is not re-read by a separate dropout kernel.  Two vectors in flight per thread.
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ldgu, bf16* __restrict__ h, long long ldh,
                                                          int M, int F, bf16* __restrict__ hd, long long ldhd,
-                                                         const uint32_t* __restrict__ seed_ptr, uint32_t key, uint32_t thr16, float inv_keep) {
+                                                         const uint32_t* __restrict__ seed_ptr, uint32_t key, uint32_t thr16, float inv_keep,
+                                                         Fp8Out f8) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float q_inv = f8.q != nullptr ? *f8.inv_scale : 0.f;
+  float q_max = 0.f;
   const int fv = F / 8;
   const long long total = (long long)M * fv;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -305,6 +320,12 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
       for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
       const bf16x8 packed = pack8(o);
       *reinterpret_cast<bf16x8*>(h + row * ldh + c) = packed;
+      if (f8.q != nullptr) {
+        float ob8[8];
+        unpack8(packed, ob8);
+        *reinterpret_cast<uint2*>(f8.q + row * f8.ld + c) = pack8_e4m3(ob8, q_inv);
+        q_max = fmaxf(q_max, absmax8(ob8));
+      }
       if (hd != nullptr) {
         float ob[8], d[8];
         unpack8(packed, ob);  // the mask multiplies the rounded activation, exactly like dropout_expand(h)
@@ -314,9 +335,12 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
       }
     }
   }
+  if (f8.q != nullptr) amax_commit(q_max, f8.amax);
 }
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ gu,
                                                          long long ldgu, bf16* __restrict__ dgu, long long lddgu, int M, int F) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int fv = F / 8;
   const long long total = (long long)M * fv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -338,11 +362,11 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
   }
 }
 void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, void* hd, long long ldhd,
-                const uint32_t* seed_ptr, uint32_t key, uint32_t thr16, float inv_keep, cudaStream_t s) {
+                const uint32_t* seed_ptr, uint32_t key, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s) {
   if (F % 8 || ldgu % 8 || ldh % 8 || (hd != nullptr && ldhd % 8)) throw std::runtime_error("swiglu: F and leading dims must be multiples of 8");
   const long long total = (long long)M * (F / 8);
   const int grid = (int)std::min<long long>((total + 511) / 512, (long long)num_sms() * 8);
-  swiglu_fwd_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>((const bf16*)gu, ldgu, (bf16*)h, ldh, M, F, (bf16*)hd, ldhd, seed_ptr, key, thr16, inv_keep);
+  launch_k(swiglu_fwd_kernel, grid > 0 ? grid : 1, 256, 0, s, (const bf16*)gu, ldgu, (bf16*)h, ldh, M, F, (bf16*)hd, ldhd, seed_ptr, key, thr16, inv_keep, f8);
   RB_CHECK_LAUNCH("swiglu_fwd");
 }
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,
@@ -350,13 +374,15 @@ void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, 
   if (F % 8 || ldgu % 8 || lddh % 8 || lddgu % 8) throw std::runtime_error("swiglu_bwd: dims must be multiples of 8");
   const long long total = (long long)M * (F / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-  swiglu_bwd_kernel<<<grid, 256, 0, s>>>((const bf16*)dh, lddh, (const bf16*)gu, ldgu, (bf16*)dgu, lddgu, M, F);
+  launch_k(swiglu_bwd_kernel, grid, 256, 0, s, (const bf16*)dh, lddh, (const bf16*)gu, ldgu, (bf16*)dgu, lddgu, M, F);
   RB_CHECK_LAUNCH("swiglu_bwd");
 }
 
 // ============================================================================================ embedding
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
                                                             bf16* __restrict__ out, long long total, int hv) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / hv;
     const int c = int(i % hv);
@@ -365,6 +391,8 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __res
 }
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dout,
                                                             float* __restrict__ dtable, long long total, int hv, long long padding_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / hv;
     const int c = int(i % hv);
@@ -381,14 +409,14 @@ void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int 
   if (H % 8) throw std::runtime_error("embedding: H must be a multiple of 8");
   const long long total = (long long)M * (H / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-  embedding_fwd_kernel<<<grid, 256, 0, s>>>(ids, (const bf16*)table, (bf16*)out, total, H / 8);
+  launch_k(embedding_fwd_kernel, grid, 256, 0, s, ids, (const bf16*)table, (bf16*)out, total, H / 8);
   RB_CHECK_LAUNCH("embedding_fwd");
 }
 void embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int M, int H, long long padding_idx, cudaStream_t s) {
   if (H % 8) throw std::runtime_error("embedding: H must be a multiple of 8");
   const long long total = (long long)M * (H / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-  embedding_bwd_kernel<<<grid, 256, 0, s>>>(ids, (const bf16*)dout, dtable, total, H / 8, padding_idx);
+  launch_k(embedding_bwd_kernel, grid, 256, 0, s, ids, (const bf16*)dout, dtable, total, H / 8, padding_idx);
   RB_CHECK_LAUNCH("embedding_bwd");
 }
 
@@ -431,6 +459,8 @@ void add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t
 }
 
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long nv, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
     float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
@@ -441,7 +471,7 @@ void cast_f32_to_bf16(const float* in, void* out, long long n, float scale, cuda
   if (n % 8) throw std::runtime_error("cast: n must be a multiple of 8");
   const long long nv = n / 8;
   const int grid = (int)std::min<long long>((nv + 255) / 256, (long long)num_sms() * 8);
-  cast_kernel<<<grid, 256, 0, s>>>(in, (bf16*)out, nv, scale);
+  launch_k(cast_kernel, grid, 256, 0, s, in, (bf16*)out, nv, scale);
   RB_CHECK_LAUNCH("cast");
 }
 
@@ -460,9 +490,11 @@ void fill_uniform_hash(void* out, int R, int C, long long ld, uint32_t seed, flo
   RB_CHECK_LAUNCH("fill_uniform");
 }
 
-__global__ void seed_advance_kernel(uint32_t* seed) { *seed = lowbias32(*seed + 0x9E3779B9u); }
+__global__ void seed_advance_kernel(uint32_t* seed) {
+  pdl_wait();
+  pdl_launch_dependents(); *seed = lowbias32(*seed + 0x9E3779B9u); }
 void seed_advance(uint32_t* seed, cudaStream_t s) {
-  seed_advance_kernel<<<1, 1, 0, s>>>(seed);
+  launch_k(seed_advance_kernel, 1, 1, 0, s, seed);
   RB_CHECK_LAUNCH("seed_advance");
 }
 

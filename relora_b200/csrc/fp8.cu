@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256) amax_kernel(const bf16* __restrict__ x, l
 // out = sat_e4m3(x * inv_scale); optionally records amax(|x|) into *amax_cur
 __global__ void __launch_bounds__(256) quantize_kernel(const bf16* __restrict__ x, long long ld, uint8_t* __restrict__ out, long long ld8,
                                                        int R, int C, const float* __restrict__ inv_scale, float* __restrict__ amax_cur) {
+  pdl_wait();
+  pdl_launch_dependents();
   const float inv = *inv_scale;
   const int cv = C / 16;
   const long long total = (long long)R * cv;
@@ -79,6 +81,8 @@ __global__ void weight_scale_kernel(const float* __restrict__ amax, float* __res
 // per activation site i: state[i] = {amax of the previous micro-step, amax being recorded}
 __global__ void prep_kernel(float* __restrict__ state, const float* __restrict__ w_scale, float* __restrict__ inv_sx,
                             float* __restrict__ alpha_main, float* __restrict__ alpha_inv, int n, float margin) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float cur = state[2 * i + 1];
@@ -111,13 +115,13 @@ void fp8_quantize_weight(const void* w, long long ld, void* w8, long long ld8, i
 void fp8_quantize_act(const void* x, long long ld, void* x8, long long ld8, int R, int C, const float* inv_scale, float* amax_cur,
                       cudaStream_t s) {
   if (C % 16 != 0 || ld % 8 != 0 || ld8 % 16 != 0) throw std::runtime_error("fp8_quantize_act: columns must be a multiple of 16");
-  quantize_kernel<<<grid_for((long long)R * C / 16), 256, 0, s>>>((const bf16*)x, ld, (uint8_t*)x8, ld8, R, C, inv_scale, amax_cur);
+  launch_k(quantize_kernel, grid_for((long long)R * C / 16), 256, 0, s, (const bf16*)x, ld, (uint8_t*)x8, ld8, R, C, inv_scale, amax_cur);
   RB_CHECK_LAUNCH("fp8_quantize_act");
 }
 
 void fp8_prep(float* state, const float* w_scale, float* inv_sx, float* alpha_main, float* alpha_inv, int n, float margin,
               cudaStream_t s) {
-  prep_kernel<<<(n + 127) / 128, 128, 0, s>>>(state, w_scale, inv_sx, alpha_main, alpha_inv, n, margin);
+  launch_k(prep_kernel, (n + 127) / 128, 128, 0, s, state, w_scale, inv_sx, alpha_main, alpha_inv, n, margin);
   RB_CHECK_LAUNCH("fp8_prep");
 }
 

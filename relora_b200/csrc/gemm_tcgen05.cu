@@ -147,6 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a1);
@@ -184,6 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();  // everything above is CTA-local: it overlaps the tail of the previous kernel in the stream (PDL)
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_work = num_tiles * p.split_k;
@@ -645,6 +647,7 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_w);
@@ -673,6 +676,7 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_lora = p.r / BLOCK_K;                     // r is a multiple of 64
@@ -1100,13 +1104,15 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   if (PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     check(cudaLaunchKernelEx(&cfg, kern, ma1, mb1, ma2, mb2, mout, mres, p), "cudaLaunchKernelEx(gemm pair)");
   } else {
-    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ma1, mb1, ma2, mb2, mout, mres, p);
+    launch_k(kern, grid, kNumThreads, L::kTotal, stream, ma1, mb1, ma2, mb2, mout, mres, p);
   }
   RB_CHECK_LAUNCH("gemm_kernel");
 }
@@ -1174,7 +1180,7 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(m_dy, m_w, m_du, m_a, m_out, p);
+  launch_k(kern, grid, kNumThreads, L::kTotal, stream, m_dy, m_w, m_du, m_a, m_out, p);
   RB_CHECK_LAUNCH("lora_dx_kernel");
 }
 

@@ -3,13 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fp8out.h"
+
 namespace rb {
 
 // ---- norms ---------------------------------------------------------------------------------
 // y = w * bf16(x * rstd),  rstd = rsqrt(mean(x^2) + eps).  Optionally also writes G dropout-masked copies
 // xd[m, g*H + k] = keep(seed_g, m, k) ? y[m,k] / (1-p) : 0   (inputs of the LoRA down-projections).
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, cudaStream_t s);
+                 const uint32_t* seed_ptr, const uint32_t* keys, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s);
 // dx = rstd * (g - xhat * mean(g * xhat)) with g = dy * w (+ dx_add);  dw_f32[H] += sum_m dy * bf16(xhat)
 // `ws` (fp32 [rmsnorm_bwd_ws_blocks(), H]) + `ticket` (zeroed uint32) enable the warp-per-row kernel (H <= 2048); without
 // them the block-per-row fallback with global atomics on dw is used.
@@ -17,13 +19,13 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
                  int M, int H, float* ws, unsigned int* ticket, cudaStream_t s);
 int rmsnorm_bwd_ws_blocks();
 bool rmsnorm_fwd_warp(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, cudaStream_t s);
+                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s);
 bool rmsnorm_bwd_warp(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add, void* dx, float* dw, int M,
                       int H, float* ws, unsigned int* ticket, cudaStream_t s);
 
 // xd[m, g*H + k] = keep(seed_g, m, k) ? x[m,k] / (1-p) : 0
 void dropout_expand(const void* x, void* xd, int M, int H, int G, const uint32_t* seed_ptr, const uint32_t* keys,
-                    uint32_t thr16, float inv_keep, cudaStream_t s);
+                    uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s);
 // out[m,k] = base[m,k] + sum_g keep(seed_g, m, k) * part_g[m,k] / (1-p)        (backward through the LoRA dropout)
 // part_g[m,k] = parts[g*part_stride + m*ld_parts + k]
 void dropout_combine(const void* base, const void* parts, long long part_stride, long long ld_parts, void* out, int M, int H, int G,
@@ -46,7 +48,7 @@ void rope_pack_bwd(const void* dq, const void* dk, const void* dv, long long sB,
 // gu: [M, 2F] (gate | up) -> h[M, F] = silu(gate) * up
 // optional hd[M, F] = keep(mix(seed, key); row, col) ⊙ h / (1-p): the dropout-expanded copy for the next LoRA down-projection
 void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, int F, void* hd, long long ldhd,
-                const uint32_t* seed_ptr, uint32_t key, uint32_t thr16, float inv_keep, cudaStream_t s);
+                const uint32_t* seed_ptr, uint32_t key, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s);
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,
                 cudaStream_t s);
 

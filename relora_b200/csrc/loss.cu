@@ -11,6 +11,8 @@ namespace rb {
 __global__ void __launch_bounds__(512) ce_kernel(bf16* __restrict__ logits, long long ld, const int64_t* __restrict__ labels, int V,
                                                  float grad_scale, long long ignore_index, float* __restrict__ loss_sum,
                                                  float* __restrict__ count) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t ce_smem[];
   bf16* row_s = reinterpret_cast<bf16*>(ce_smem);
   __shared__ float scratch[32];
@@ -82,7 +84,7 @@ void cross_entropy_fwd_bwd(void* logits, long long ld, const int64_t* labels, in
     check(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(ce)");
     configured = smem;
   }
-  ce_kernel<<<M, 512, smem, s>>>((bf16*)logits, ld, labels, V, grad_scale, ignore_index, loss_sum, count);
+  launch_k(ce_kernel, M, 512, smem, s, (bf16*)logits, ld, labels, V, grad_scale, ignore_index, loss_sum, count);
   RB_CHECK_LAUNCH("cross_entropy");
 }
 

@@ -13,7 +13,9 @@ constexpr int kWarpsPerBlock = 8;
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
     const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, float* __restrict__ rstd_out, int M, int H, float eps,
-    bf16* __restrict__ xd, int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16, float inv_keep) {
+    bf16* __restrict__ xd, int G, const uint32_t* __restrict__ seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, Fp8Out f8) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * kWarpsPerBlock + warp;
   if (row >= M) return;
@@ -42,6 +44,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
   }
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * H);
+  const float q_inv = f8.q != nullptr ? *f8.inv_scale : 0.f;
+  float q_max = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + i * 32;
@@ -52,6 +56,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = bf16_round(wf[j] * bf16_round(f[j] * rstd));
       yr[c] = pack8(o);
+      if (f8.q != nullptr) {
+        *reinterpret_cast<uint2*>(f8.q + (long long)row * f8.ld + c * 8) = pack8_e4m3(o, q_inv);
+        q_max = fmaxf(q_max, absmax8(o));
+      }
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
         const uint32_t sd = g == 0 ? s0 : (g == 1 ? s1 : (g == 2 ? s2 : s3));
@@ -62,6 +70,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_fwd_warp_kernel(
       }
     }
   }
+  if (f8.q != nullptr) amax_commit(q_max, f8.amax);
 }
 
 template <int VPL>
@@ -69,6 +78,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmsnorm_bwd_warp_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ rstd,
     const bf16* __restrict__ dx_add, bf16* __restrict__ dx, float* __restrict__ dw, int M, int H) {
   extern __shared__ float sdw[];  // [H] block partial of dw
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = H / 8;
   for (int c = threadIdx.x; c < H; c += blockDim.x) sdw[c] = 0.f;
@@ -175,13 +186,13 @@ static int pick_vpl(int nvec) {
 }
 
 bool rmsnorm_fwd_warp(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps, void* xd, int G,
-                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, cudaStream_t s) {
+                      const uint32_t* seed_ptr, uint4 keys, uint32_t thr16, float inv_keep, Fp8Out f8, cudaStream_t s) {
   const int vpl = pick_vpl(H / 8);
   if (vpl == 0) return false;
   const int grid = ceil_div(M, kWarpsPerBlock);
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)w;
   bf16 *yp = (bf16*)y, *xdp = (bf16*)xd;
-#define L(V) rmsnorm_fwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, keys, thr16, inv_keep)
+#define L(V) launch_k(rmsnorm_fwd_warp_kernel<V>, grid, kWarpsPerBlock * 32, 0, s, xp, wp, yp, rstd, M, H, eps, xdp, G, seed_ptr, keys, thr16, inv_keep, f8)
   switch (vpl) {
     case 1: L(1); break;
     case 2: L(2); break;
@@ -219,7 +230,7 @@ bool rmsnorm_bwd_warp(const void* dy, const void* x, const void* w, const float*
   }
   const int grid = std::min(ceil_div(M, kWarpsPerBlock), occ[vpl] * num_sms());
   const bf16 *a = (const bf16*)dy, *b = (const bf16*)x, *c = (const bf16*)w, *d = (const bf16*)dx_add;
-#define L(V) rmsnorm_bwd_warp_kernel<V><<<grid, kWarpsPerBlock * 32, smem, s>>>(a, b, c, rstd, d, (bf16*)dx, dw, M, H)
+#define L(V) launch_k(rmsnorm_bwd_warp_kernel<V>, grid, kWarpsPerBlock * 32, smem, s, a, b, c, rstd, d, (bf16*)dx, dw, M, H)
   switch (vpl) {
     case 1: L(1); break;
     case 2: L(2); break;

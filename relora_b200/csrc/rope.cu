@@ -28,6 +28,8 @@ __device__ __forceinline__ void rotate8(const uint4& a, const uint4& b, const ui
 __global__ void __launch_bounds__(256) rope_vec_kernel(bf16* __restrict__ buf, long long ld, long long total, int T, int n_heads, int hd,
                                                        int half, const bf16* __restrict__ cosp, const bf16* __restrict__ sinp, float sgn,
                                                        int pos0) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int nr = half / 8;  // vectors per half
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = int(i % nr);
@@ -51,7 +53,7 @@ bool rope_inplace_vec(void* buf, long long ld, int M, int T, int n_rot_heads, in
   if (half % 8 != 0 || hd % 8 != 0 || ld % 8 != 0 || (reinterpret_cast<uintptr_t>(buf) & 15) != 0) return false;
   const long long total = (long long)M * n_rot_heads * (half / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
-  rope_vec_kernel<<<grid, 256, 0, s>>>((bf16*)buf, ld, total, T, n_rot_heads, hd, half, (const bf16*)cos, (const bf16*)sin,
+  launch_k(rope_vec_kernel, grid, 256, 0, s, (bf16*)buf, ld, total, T, n_rot_heads, hd, half, (const bf16*)cos, (const bf16*)sin,
                                        backward ? -1.f : 1.f, pos0);
   RB_CHECK_LAUNCH("rope_vec");
   return true;
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256) rope_pack_bwd_kernel(const bf16* __restri
                                                             long long sB, long long sH, long long sT, bf16* __restrict__ out, long long ldo,
                                                             long long total, int T, int nh, int hd, int half, const bf16* __restrict__ cosp,
                                                             const bf16* __restrict__ sinp, int pos0) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int nv = hd / 8, nr = half / 8;
   const long long hsz = (long long)nh * hd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -98,7 +102,7 @@ void rope_pack_bwd(const void* dq, const void* dk, const void* dv, long long sB,
     throw std::runtime_error("rope_pack_bwd: head_dim / rotary_dim / strides must allow 128-bit accesses");
   const long long total = (long long)B * T * nh * (hd / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
-  rope_pack_bwd_kernel<<<grid, 256, 0, s>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, sB, sH, sT, (bf16*)out, ldo, total, T, nh, hd,
+  launch_k(rope_pack_bwd_kernel, grid, 256, 0, s, (const bf16*)dq, (const bf16*)dk, (const bf16*)dv, sB, sH, sT, (bf16*)out, ldo, total, T, nh, hd,
                                             half, (const bf16*)cos, (const bf16*)sin, pos0);
   RB_CHECK_LAUNCH("rope_pack_bwd");
 }

@@ -350,7 +350,13 @@ class FusedLlamaStepper:
             o = F_.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=True)
         return o.detach().transpose(1, 2).reshape(self.M_, self.h)
 
-    def _lora_group_fwd(self, xn, xd, A, B, W, u, out, *, G, K, Ng, residual=None, site=None):
+    def _q8(self, l, s_i, K):
+        """(q8, inv_scale, amax_cur) arguments that make a producer kernel also emit the E4M3 copy of its output."""
+        if not self.fp8:
+            return (None, None, None)
+        return (self.x8_h if K == self.h else self.x8_f, self.inv_sx[l, s_i:s_i + 1], self.act_state[l, s_i, 1:2])
+
+    def _lora_group_fwd(self, xn, xd, A, B, W, u, out, *, G, K, Ng, residual=None, site=None, prequant=False):
         """u = s·xd_g·A_gᵀ (grouped) ; out = [xn | u]·[W | B]ᵀ (+ residual).
 
         fp8 path (``site = (layer, index)``): xn is quantised to E4M3 with the site's delayed scale and multiplied with the E4M3
@@ -361,7 +367,8 @@ class FusedLlamaStepper:
         if self.fp8 and site is not None:
             l, s_i = site
             x8 = self.x8_h if K == self.h else self.x8_f
-            self.C.fp8_quantize_act(xn, x8, self.inv_sx[l, s_i:s_i + 1], self.act_state[l, s_i, 1:2])
+            if not prequant:  # the producer of xn did not emit the E4M3 copy itself
+                self.C.fp8_quantize_act(xn, x8, self.inv_sx[l, s_i:s_i + 1], self.act_state[l, s_i, 1:2])
         if self.fp8 and site is not None and not self._fp8_calibrating:
             g(xd, A, u, M=M, N=G * r, K1=K, n_per_group=r, a1_group_kofs=K if drop else 0, alpha=self.scale,
               alpha_dev=self.alpha_inv[l, s_i:s_i + 1])
@@ -386,43 +393,43 @@ class FusedLlamaStepper:
             # ---- attention block
             if p > 0:
                 xd = self.xd_qkv[sl]
-                C.rmsnorm_fwd(x, S.w1, self.xn, self.rstd1[sl], self.eps, xd, seed, S.keys_qkv, p)
+                C.rmsnorm_fwd(x, S.w1, self.xn, self.rstd1[sl], self.eps, xd, seed, S.keys_qkv, p, *self._q8(l, 0, h))
                 xn = self.xn
             else:
                 xn = self.xd_qkv[sl][:, :h] if self.p == 0 else self.xn  # p==0: the normed input is what dA needs
                 xn = xn if xn.is_contiguous() else self.xn
                 C.rmsnorm_fwd(x, S.w1, xn, self.rstd1[sl], self.eps, None, None, [], 0.0)
                 xd = xn
-            self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h, site=(l, 0))
+            self._lora_group_fwd(xn, xd, S.A_qkv, S.B_qkv, S.Wqkv, self.u_qkv[sl], qkv, G=3, K=h, Ng=h, site=(l, 0), prequant=p > 0)
             C.rope_inplace(qkv, self.T_, 2 * self.nh, self.hd, self.hd, self.cos, self.sin, False, 0)
             attn = self._attention(qkv, train, sl)
             if p > 0:
                 xd_o = self.xd_o[sl]
-                C.dropout_expand(attn, xd_o, seed, [S.key_o], p)
+                C.dropout_expand(attn, xd_o, seed, [S.key_o], p, *self._q8(l, 1, h))
             else:
                 xd_o = attn
                 if train:
                     self.xd_o[sl].copy_(attn)
-            self._lora_group_fwd(attn, xd_o, S.A_o, S.B_o, S.Wo, self.u_o[sl], x1, G=1, K=h, Ng=h, residual=x, site=(l, 1))
+            self._lora_group_fwd(attn, xd_o, S.A_o, S.B_o, S.Wo, self.u_o[sl], x1, G=1, K=h, Ng=h, residual=x, site=(l, 1), prequant=p > 0)
             # ---- MLP block
             if p > 0:
                 xd = self.xd_gu[sl]
-                C.rmsnorm_fwd(x1, S.w2, self.xn, self.rstd2[sl], self.eps, xd, seed, S.keys_gu, p)
+                C.rmsnorm_fwd(x1, S.w2, self.xn, self.rstd2[sl], self.eps, xd, seed, S.keys_gu, p, *self._q8(l, 2, h))
                 xn = self.xn
             else:
                 xn = self.xd_gu[sl] if self.p == 0 else self.xn
                 C.rmsnorm_fwd(x1, S.w2, xn, self.rstd2[sl], self.eps, None, None, [], 0.0)
                 xd = xn
-            self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f, site=(l, 2))
+            self._lora_group_fwd(xn, xd, S.A_gu, S.B_gu, S.Wgu, self.u_gu[sl], gu, G=2, K=h, Ng=f, site=(l, 2), prequant=p > 0)
             if p > 0:
                 xd_d = self.xd_d[sl]
-                C.swiglu_fwd(gu, self.hmid, xd_d, seed, S.key_d, p)  # activation + its dropout-expanded copy in one pass
+                C.swiglu_fwd(gu, self.hmid, xd_d, seed, S.key_d, p, *self._q8(l, 3, f))  # activation, dropout copy (and E4M3 copy)
             else:
-                C.swiglu_fwd(gu, self.hmid)
+                C.swiglu_fwd(gu, self.hmid, None, None, 0, 0.0, *self._q8(l, 3, f))
                 xd_d = self.hmid
                 if train:
                     self.xd_d[sl].copy_(self.hmid)
-            self._lora_group_fwd(self.hmid, xd_d, S.A_d, S.B_d, S.Wd, self.u_d[sl], x_next, G=1, K=f, Ng=h, residual=x1, site=(l, 3))
+            self._lora_group_fwd(self.hmid, xd_d, S.A_d, S.B_d, S.Wd, self.u_d[sl], x_next, G=1, K=f, Ng=h, residual=x1, site=(l, 3), prequant=True)
         x_last = self.x_in[self.L] if train else self.x_in[self.L % 2]
         C.rmsnorm_fwd(x_last, self.w_norm, self.xf, self.rstd_f, self.eps, None, None, [], 0.0)
         return x_last

@@ -598,3 +598,41 @@ def test_gemm_fp8_frozen_path_with_bf16_lora_branch(C, F, M, N, K, pair):
     # and it is close to the unquantised product (quantisation noise only)
     full = x.float() @ W.float().t() + u.float() @ B.float().t() + res.float()
     assert _relerr(out, full) < 0.06
+
+
+def test_producers_emit_the_same_e4m3_copy_as_the_standalone_quantiser(C):
+    """RMSNorm / SwiGLU / dropout_expand can write the E4M3 copy of their output themselves (fp8 frozen-weight path):
+    bit-identical to quantising the bf16 output afterwards, same recorded amax."""
+    torch.manual_seed(0)
+    f32 = lambda v: torch.tensor([v], dtype=torch.float32, device="cuda")  # noqa: E731
+    M, H, Fd = 300, 768, 2560
+    seed = torch.tensor([31], dtype=torch.int32, device="cuda")
+    inv = f32(448.0 / 6.0)
+
+    def ref_q(y):
+        q, am = torch.empty(y.shape, dtype=torch.uint8, device="cuda"), f32(0.0)
+        C.fp8_quantize_act(y, q, inv, am)
+        return q, float(am)
+
+    # RMSNorm (+ 2 dropout copies)
+    x, w = _rand(M, H), (1.0 + 0.1 * torch.randn(H, device="cuda")).to(BF)
+    y, rstd = torch.empty_like(x), torch.empty(M, device="cuda", dtype=torch.float32)
+    xd = torch.empty(M, 2 * H, device="cuda", dtype=BF)
+    q, am = torch.empty(M, H, dtype=torch.uint8, device="cuda"), f32(0.0)
+    C.rmsnorm_fwd(x, w, y, rstd, 1e-6, xd, seed, [1, 2], 0.1, q, inv, am)
+    rq, ram = ref_q(y)
+    assert torch.equal(q, rq) and float(am) == ram
+    # SwiGLU (+ dropout copy)
+    gu = _rand(M, 2 * Fd)
+    h, hd = torch.empty(M, Fd, device="cuda", dtype=BF), torch.empty(M, Fd, device="cuda", dtype=BF)
+    q, am = torch.empty(M, Fd, dtype=torch.uint8, device="cuda"), f32(0.0)
+    C.swiglu_fwd(gu, h, hd, seed, 5, 0.1, q, inv, am)
+    rq, ram = ref_q(h)
+    assert torch.equal(q, rq) and float(am) == ram
+    # dropout_expand: E4M3 copy of the un-dropped input
+    a = _rand(M, H)
+    ad = torch.empty(M, H, device="cuda", dtype=BF)
+    q, am = torch.empty(M, H, dtype=torch.uint8, device="cuda"), f32(0.0)
+    C.dropout_expand(a, ad, seed, [7], 0.1, q, inv, am)
+    rq, ram = ref_q(a)
+    assert torch.equal(q, rq) and float(am) == ram
