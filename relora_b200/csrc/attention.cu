@@ -13,6 +13,8 @@
 // operand (reduction over head_dim) and as an MN-major operand (reduction over its rows) by descriptor alone.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -32,7 +34,19 @@ constexpr int BQ = 128;  // rows owned by the row threads (queries in fwd / dq, 
 constexpr int BK = 64;   // columns per step (keys in fwd / dq, queries in dkv)
 constexpr int kTile128 = 128 * 128;  // bytes of a [128 x 64] bf16 tile
 constexpr int kTile64 = 64 * 128;    // bytes of a [64 x 64] bf16 tile
-constexpr int kThreads = 160;
+// The driver keeps kernels that allocate tensor memory at one resident CTA per SM (occupancy calculator: 1, independent of
+// shared memory and registers), so the latency hiding comes from several independent "groups" inside one CTA: each group is
+// 4 row warps + 1 control warp working on its own (batch, head, block) item with its own shared-memory region, barriers and
+// tensor-memory columns.
+#ifndef RB_ATTN_GROUPS_FWD
+#define RB_ATTN_GROUPS_FWD 1
+#define RB_ATTN_GROUPS_BWD 1
+#endif
+constexpr int kFwdGroups = RB_ATTN_GROUPS_FWD, kDqGroups = RB_ATTN_GROUPS_BWD, kDkvGroups = RB_ATTN_GROUPS_BWD;  // measured: 3/2/2 groups per CTA 88 / 232 us vs 1 group (several CTAs per SM) 79 / 210 us
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+constexpr int kFwdGroupBytes = 2 * kTile128 + 4 * kTile64 + 1024;                  // Q, K/V stages, P, barriers
+constexpr int kDqGroupBytes = 3 * kTile128 + 4 * kTile64 + 1024;                   // Q, dO, K/V stages, dS, barriers
+constexpr int kDkvGroupBytes = 4 * kTile128 + 4 * kTile64 + 1024 + 1024;           // K, V, Q/dO stages, Pt, dSt, lse/delta, barriers
 constexpr float kNegInf = -1e30f;
 
 __device__ __forceinline__ uint64_t desc_k(const uint8_t* tile, int kstep) {  // K-major operand, 16 columns per MMA
@@ -40,6 +54,20 @@ __device__ __forceinline__ uint64_t desc_k(const uint8_t* tile, int kstep) {  //
 }
 __device__ __forceinline__ uint64_t desc_mn(const uint8_t* tile, int kstep) {  // MN-major operand, 16 rows per MMA
   return make_desc_sw128(smem_u32(tile) + kstep * 2048, 8192, 1024);
+}
+
+#ifndef RB_ATTN_SLEEP_NS
+#define RB_ATTN_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void attn_wait(uint64_t* bar, uint32_t parity) {
+  if constexpr (RB_ATTN_SLEEP_NS > 0) mbar_wait_sleep(bar, parity, RB_ATTN_SLEEP_NS);
+  else mbar_wait(bar, parity);
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2, no range fix-up (inputs are <= ~8, -inf -> 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // row `r` of a [128 x 64] bf16 tile (128-byte swizzle): 8 chunks of 8 values
@@ -76,9 +104,15 @@ struct FwdArgs {
 };
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdArgs p) {
+__global__ void __launch_bounds__((4 * kFwdGroups + kFwdGroups) * 32, kFwdGroups == 1 ? 3 : 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdArgs p) {
+  constexpr int NG = kFwdGroups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const bool is_ctrl = warp >= 4 * NG;
+  const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem0 + g * kFwdGroupBytes;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kTile128;      // 2 stages
   uint8_t* sV = sK + 2 * kTile64;   // 2 stages
@@ -90,18 +124,21 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
   uint64_t* s_full = bars + 5;
   uint64_t* p_ready = bars + 6;
   uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem0 + 2 * kTile128 + 4 * kTile64 + 64);  // in group 0's barrier page
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) pdl_launch_dependents();
-  const int qb = gridDim.x - 1 - blockIdx.x;  // long (late) query blocks first
-  const int head = blockIdx.y, b = blockIdx.z;
+  // work item of this group: (query block, head, batch), heaviest (latest) query blocks first
+  const int nqb = (p.T + BQ - 1) / BQ;
+  const long long per = (long long)p.B * p.nh;
+  const long long item = (long long)blockIdx.x * NG + g;
+  const bool active = item < per * nqb;
+  const int qb = active ? nqb - 1 - int(item / per) : 0;
+  const int head = int((item % per) % p.nh), b = active ? int((item % per) / p.nh) : 0;
   const int t0 = qb * BQ;
   const int kv_end = min(p.T, t0 + BQ);
-  const int n_kv = (kv_end + BK - 1) / BK;
+  const int n_kv = active ? (kv_end + BK - 1) / BK : 0;
   const int row0 = b * p.T;
 
-  if (threadIdx.x == 128) {
+  if (is_ctrl && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -113,18 +150,18 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
     fence_barrier_init();
     tma_prefetch_desc(&map_qkv);
   }
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, 128);  // S: columns 0-63, O partial: columns 64-127
+  if (warp == 4 * NG) {
+    tmem_alloc(tmem_slot, pow2_cols(NG * 128));  // per group: S in columns 0-63, O in columns 64-127
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot + g * 128;
   pdl_wait();
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (is_ctrl) {
+    if (lane == 0 && active) {
       auto load_kv = [&](int jj, int st) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
         tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
@@ -142,66 +179,82 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
         for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_s, k != 0);
         umma_commit(s_full);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      attn_wait(q_full, 0);
+      attn_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_s(0);
       for (int jj = 0; jj < n_kv; ++jj) {
         const int st = jj & 1;
-        mbar_wait(p_ready, jj & 1);
+        attn_wait(p_ready, jj & 1);
         tc_fence_after();
+        // the scores of the next step first (the row threads are done with S once p_ready fired): their latency is what the
+        // row threads wait for; then this step's P·V, whose completion (o_full) only gates the reuse of P and a rescale of O
+        if (jj + 1 < n_kv) {
+          attn_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(st ^ 1);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tmem_base + 64, desc_k(sP, k), desc_mn(sV + st * kTile64, k), idesc_pv, (jj | k) != 0);  // O accumulates in TMEM
+        umma_commit(o_full);
         umma_commit(&kv_free[st]);
-        if (jj + 1 < n_kv) {
-          mbar_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s(st ^ 1);  // its commit also covers the P·V above: s_full(j+1) => O holds steps <= j and P is free again
-        } else {
-          umma_commit(o_full);
-        }
         if (jj + 2 < n_kv) {
-          mbar_wait(&kv_free[st], (jj >> 1) & 1);
+          attn_wait(&kv_free[st], (jj >> 1) & 1);
           load_kv(jj + 2, st);
         }
       }
     }
   } else {
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127;
     const int t = t0 + r;
-    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, 0);
     // The output accumulates in tensor memory across key steps.  The running maximum used for the exponentials ("m") is
     // only raised -- and O rescaled by a TMEM load / multiply / store -- when a step's maximum exceeds it by more than
     // 2^8; any reference maximum is mathematically valid as long as exp2 stays in range, and the same m enters l.
     float m = kNegInf, l = 0.f;
-    const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define ATR(slot) do { if (tr) p.trace[(slot) * 64 + jj] = clock64(); } while (0)
     if (tr) p.trace[7 * 64] = clock64();
     for (int jj = 0; jj < n_kv; ++jj) {
       const int k0 = jj * BK;
       ATR(0);
-      mbar_wait(s_full, jj & 1);
+      attn_wait(s_full, jj & 1);
       tc_fence_after();
       ATR(1);
       float s[64];
       ld64(lane_addr, s);
       ATR(2);
       const bool edge = (k0 + BK - 1 > t0) || (k0 + BK > p.T);  // diagonal block or ragged tail (uniform in the CTA)
-      float mx = kNegInf;
+      float mx = kNegInf;  // maxima are tracked on the raw scores; the softmax scale is folded into the exp2 argument
+      if (edge) {
+        const int lim = min(t, p.T - 1) - k0;  // last valid column of this row in the block
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = s[c] * p.scale_log2;
-        if (edge && (k0 + c > t || k0 + c >= p.T)) v = kNegInf;
-        s[c] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 64; ++c) {
+          s[c] = c <= lim ? s[c] : kNegInf;
+          mx = fmaxf(mx, s[c]);
+        }
+      } else {
+        float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];  // four independent chains instead of one 64-deep dependency
+#pragma unroll
+        for (int c = 4; c < 64; c += 4) {
+          m0 = fmaxf(m0, s[c]);
+          m1 = fmaxf(m1, s[c + 1]);
+          m2 = fmaxf(m2, s[c + 2]);
+          m3 = fmaxf(m3, s[c + 3]);
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      if (jj > 0) {  // P (and O, for the rescale below) are free once the previous step's P·V has completed
+        attn_wait(o_full, (jj - 1) & 1);
+        tc_fence_after();
       }
       if (jj == 0) {
         m = mx;  // first step: P·V overwrites O (accumulate = 0), nothing to rescale
-      } else if (__any_sync(0xffffffffu, mx > m + 8.0f)) {
-        // rare: bring this warp's rows of O (complete through step jj-1, see issue_s) to the new reference maximum
+      } else if (__any_sync(0xffffffffu, (mx - m) * p.scale_log2 > 8.0f)) {
+        // rare: bring this warp's rows of O to the new reference maximum
         const float m_new = fmaxf(m, mx);
-        const float f = exp2f(m - m_new);
+        const float f = fast_exp2((m - m_new) * p.scale_log2);
         uint32_t o0[32], o1[32];
         tmem_ld_32x32b_x32(lane_addr + 64, o0);
         tmem_ld_32x32b_x32(lane_addr + 96, o1);
@@ -217,14 +270,20 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
         l *= f;
         m = m_new;
       }
-      float sum = 0.f;
+      const float mc = m * p.scale_log2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float e = exp2f(s[c] - m);
-        s[c] = e;
-        sum += e;
+      for (int c = 0; c < 64; c += 4) {
+        s[c] = fast_exp2(fmaf(s[c], p.scale_log2, -mc));
+        s[c + 1] = fast_exp2(fmaf(s[c + 1], p.scale_log2, -mc));
+        s[c + 2] = fast_exp2(fmaf(s[c + 2], p.scale_log2, -mc));
+        s[c + 3] = fast_exp2(fmaf(s[c + 3], p.scale_log2, -mc));
+        a0 += s[c];
+        a1 += s[c + 1];
+        a2 += s[c + 2];
+        a3 += s[c + 3];
       }
-      l += sum;
+      l += (a0 + a1) + (a2 + a3);
       ATR(3);
       store_row64(sP, r, s);
       fence_proxy_async_smem();
@@ -233,11 +292,13 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
       ATR(4);
     }
 #undef ATR
-    mbar_wait(o_full, 0);
-    tc_fence_after();
     float O[64];
-    ld64(lane_addr + 64, O);
-    if (t < p.T) {
+    if (active) {
+      attn_wait(o_full, (n_kv - 1) & 1);
+      tc_fence_after();
+      ld64(lane_addr + 64, O);
+    }
+    if (active && t < p.T) {
       const float inv = 1.0f / l;
       bf16* op = p.out + (long long)(row0 + t) * p.ld_out + head * p.hd;
 #pragma unroll
@@ -249,14 +310,14 @@ __global__ void __launch_bounds__(kThreads, 3) attn_fwd_kernel(const __grid_cons
           *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
         }
       }
-      p.lse[((long long)b * p.nh + head) * p.T + t] = m + log2f(l);
+      p.lse[((long long)b * p.nh + head) * p.T + t] = m * p.scale_log2 + log2f(l);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 4 * NG) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(*tmem_slot, pow2_cols(NG * 128));
   }
 }
 
@@ -295,10 +356,16 @@ struct BwdArgs {
 };
 
 // =============================================================================================== backward: dQ
-__global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__((4 * kDqGroups + kDqGroups) * 32, kDqGroups == 1 ? 2 : 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                    const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
+  constexpr int NG = kDqGroups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const bool is_ctrl = warp >= 4 * NG;
+  const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem0 + g * kDqGroupBytes;
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + kTile128;
   uint8_t* sK = sdO + kTile128;     // 2 stages
@@ -311,18 +378,20 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
   uint64_t* sdp_full = bars + 5;
   uint64_t* ds_ready = bars + 6;
   uint64_t* dq_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem0 + 3 * kTile128 + 4 * kTile64 + 64);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) pdl_launch_dependents();
-  const int qb = gridDim.x - 1 - blockIdx.x;
-  const int head = blockIdx.y, b = blockIdx.z;
+  const int nqb = (p.T + BQ - 1) / BQ;
+  const long long per = (long long)p.B * p.nh;
+  const long long item = (long long)blockIdx.x * NG + g;
+  const bool active = item < per * nqb;
+  const int qb = active ? nqb - 1 - int(item / per) : 0;
+  const int head = int((item % per) % p.nh), b = active ? int((item % per) / p.nh) : 0;
   const int t0 = qb * BQ;
   const int kv_end = min(p.T, t0 + BQ);
-  const int n_kv = (kv_end + BK - 1) / BK;
+  const int n_kv = active ? (kv_end + BK - 1) / BK : 0;
   const int row0 = b * p.T;
 
-  if (threadIdx.x == 128) {
+  if (is_ctrl && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -335,18 +404,18 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
   }
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, 256);  // S: 0-63, dP: 64-127, dQ: 128-191
+  if (warp == 4 * NG) {
+    tmem_alloc(tmem_slot, pow2_cols(NG * 256));  // per group (256 columns): S 0-63, dP 64-127, dQ 128-191
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot + g * 256;
   pdl_wait();
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (is_ctrl) {
+    if (lane == 0 && active) {
       auto load_kv = [&](int jj, int st) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
         tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
@@ -368,41 +437,41 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
         for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sdO, k), desc_k(sV + st * kTile64, k), idesc_kk, k != 0);
         umma_commit(sdp_full);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      attn_wait(q_full, 0);
+      attn_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_sdp(0);
       for (int jj = 0; jj < n_kv; ++jj) {
         const int st = jj & 1;
-        mbar_wait(ds_ready, jj & 1);
+        attn_wait(ds_ready, jj & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tmem_base + 128, desc_k(sdS, k), desc_mn(sK + st * kTile64, k), idesc_kmn, (jj | k) != 0);
         umma_commit(&kv_free[st]);
         if (jj + 1 < n_kv) {
-          mbar_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
+          attn_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
           tc_fence_after();
           issue_sdp(st ^ 1);  // its commit also covers the dQ MMAs above: dS may be overwritten once sdp_full fires
         } else {
           umma_commit(dq_full);
         }
         if (jj + 2 < n_kv) {
-          mbar_wait(&kv_free[st], (jj >> 1) & 1);
+          attn_wait(&kv_free[st], (jj >> 1) & 1);
           load_kv(jj + 2, st);
         }
       }
     }
   } else {
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127;
     const int t = t0 + r;
-    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, 0);
     const long long stat = ((long long)b * p.nh + head) * p.T + t;
-    const float lse = t < p.T ? p.lse[stat] : 0.f;
-    const float dl = t < p.T ? p.delta[stat] : 0.f;
+    const float lse = (active && t < p.T) ? p.lse[stat] : 0.f;
+    const float dl = (active && t < p.T) ? p.delta[stat] : 0.f;
     for (int jj = 0; jj < n_kv; ++jj) {
       const int k0 = jj * BK;
-      mbar_wait(sdp_full, jj & 1);
+      attn_wait(sdp_full, jj & 1);
       tc_fence_after();
       float s[64], dp[64];
       ld64(lane_addr, s);
@@ -410,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
       const bool edge = (k0 + BK - 1 > t0) || (k0 + BK > p.T);
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        float pr = exp2f(s[c] * p.scale_log2 - lse);
+        float pr = fast_exp2(fmaf(s[c], p.scale_log2, -lse));
         if (edge && (k0 + c > t || k0 + c >= p.T)) pr = 0.f;
         s[c] = pr * (dp[c] - dl) * p.scale;
       }
@@ -419,11 +488,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(ds_ready);
     }
-    mbar_wait(dq_full, 0);
-    tc_fence_after();
     float dq[64];
-    ld64(lane_addr + 128, dq);
-    if (t < p.T) {
+    if (active) {
+      attn_wait(dq_full, 0);
+      tc_fence_after();
+      ld64(lane_addr + 128, dq);
+    }
+    if (active && t < p.T) {
       bf16* op = p.dqkv + (long long)(row0 + t) * p.ld_dqkv + head * p.hd;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -438,17 +509,23 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dq_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 4 * NG) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(*tmem_slot, pow2_cols(NG * 256));
   }
 }
 
 // =============================================================================================== backward: dK, dV
-__global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups == 1 ? 2 : 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                     const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
+  constexpr int NG = kDkvGroups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const bool is_ctrl = warp >= 4 * NG;
+  const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem0 + g * kDkvGroupBytes;
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTile128;
   uint8_t* sQ = sV + kTile128;      // 2 stages of [64 queries x 64]
@@ -464,17 +541,20 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
   uint64_t* sdp_full = bars + 5;
   uint64_t* pds_ready = bars + 6;
   uint64_t* acc_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem0 + 4 * kTile128 + 4 * kTile64 + 1024 + 64);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) pdl_launch_dependents();
-  const int kb = blockIdx.x;  // early key blocks see the most queries and are scheduled first
-  const int head = blockIdx.y, b = blockIdx.z;
+  // work item of this group: (key block, head, batch); early key blocks see the most queries and go first
+  const int nkb = (p.T + BQ - 1) / BQ;
+  const long long per = (long long)p.B * p.nh;
+  const long long item = (long long)blockIdx.x * NG + g;
+  const bool active = item < per * nkb;
+  const int kb = active ? int(item / per) : 0;
+  const int head = int((item % per) % p.nh), b = active ? int((item % per) / p.nh) : 0;
   const int kstart = kb * BQ;
-  const int n_q = (p.T - kstart + BK - 1) / BK;  // query steps of 64 starting at the block's first key
+  const int n_q = active ? (p.T - kstart + BK - 1) / BK : 0;  // query steps of 64 starting at the block's first key
   const int row0 = b * p.T;
 
-  if (threadIdx.x == 128) {
+  if (is_ctrl && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -487,18 +567,18 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
   }
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, 256);  // Sᵀ: 0-63, dPᵀ: 64-127, dV: 128-191, dK: 192-255
+  if (warp == 4 * NG) {
+    tmem_alloc(tmem_slot, pow2_cols(NG * 256));  // per group (256 columns): Sᵀ 0-63, dPᵀ 64-127, dV 128-191, dK 192-255
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot + g * 256;
   pdl_wait();
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (is_ctrl) {
+    if (lane == 0 && active) {
       auto load_q = [&](int ii, int st) {
         mbar_arrive_expect_tx(&q_full[st], 2 * kTile64);
         tma_load_3d(&map_qkv, &q_full[st], sQ + st * kTile64, 0, head, row0 + kstart + ii * BK);
@@ -520,13 +600,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
         for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sV, k), desc_k(sdO + st * kTile64, k), idesc_kk, k != 0);
         umma_commit(sdp_full);
       };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&q_full[0], 0);
+      attn_wait(kv_full, 0);
+      attn_wait(&q_full[0], 0);
       tc_fence_after();
       issue_sdp(0);
       for (int ii = 0; ii < n_q; ++ii) {
         const int st = ii & 1;
-        mbar_wait(pds_ready, ii & 1);
+        attn_wait(pds_ready, ii & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -536,22 +616,22 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
           umma_f16_ss(tmem_base + 192, desc_k(sdSt, k), desc_mn(sQ + st * kTile64, k), idesc_kmn, (ii | k) != 0);
         umma_commit(&q_free[st]);
         if (ii + 1 < n_q) {
-          mbar_wait(&q_full[st ^ 1], ((ii + 1) >> 1) & 1);
+          attn_wait(&q_full[st ^ 1], ((ii + 1) >> 1) & 1);
           tc_fence_after();
           issue_sdp(st ^ 1);
         } else {
           umma_commit(acc_full);
         }
         if (ii + 2 < n_q) {
-          mbar_wait(&q_free[st], (ii >> 1) & 1);
+          attn_wait(&q_free[st], (ii >> 1) & 1);
           load_q(ii + 2, st);
         }
       }
     }
   } else {
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127;
     const int kk = kstart + r;  // this thread's key
-    const uint32_t lane_addr = tmem_addr(tmem_base, warp * 32, 0);
+    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, 0);
     const long long stat0 = ((long long)b * p.nh + head) * p.T;
     for (int ii = 0; ii < n_q; ++ii) {
       const int q0 = kstart + ii * BK;
@@ -562,10 +642,10 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
         const float* src = r < 64 ? p.lse : p.delta;
         dst[c] = tq < p.T ? src[stat0 + tq] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + g, 128);
       const float* lse = s_lse + (ii & 1) * 64;
       const float* dl = s_dl + (ii & 1) * 64;
-      mbar_wait(sdp_full, ii & 1);
+      attn_wait(sdp_full, ii & 1);
       tc_fence_after();
       float s[64], dp[64];
       ld64(lane_addr, s);
@@ -574,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         const int tq = q0 + c;
-        float pr = exp2f(s[c] * p.scale_log2 - lse[c]);
+        float pr = fast_exp2(fmaf(s[c], p.scale_log2, -lse[c]));
         if (edge && (kk > tq || tq >= p.T || kk >= p.T)) pr = 0.f;
         s[c] = pr;
         dp[c] = pr * (dp[c] - dl[c]) * p.scale;
@@ -585,11 +665,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
       tc_fence_before();
       mbar_arrive(pds_ready);
     }
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    if (active) {
+      attn_wait(acc_full, 0);
+      tc_fence_after();
+    }
     float acc[64];
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {  // 0: dV -> v slot, 1: dK -> k slot
+    for (int which = 0; active && which < 2; ++which) {  // 0: dV -> v slot, 1: dK -> k slot
       ld64(lane_addr + 128 + which * 64, acc);
       if (kk < p.T) {
         bf16* op = p.dqkv + (long long)(row0 + kk) * p.ld_dqkv + (long long)((which == 0 ? 2 : 1) * p.nh + head) * p.hd;
@@ -607,9 +689,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_dkv_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 4 * NG) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(*tmem_slot, pow2_cols(NG * 256));
   }
 }
 
@@ -653,15 +735,18 @@ void check_shape(int B, int T, int nh, int hd) {
   if (hd % 8 != 0 || hd > 64) throw std::runtime_error("attention: head_dim must be a multiple of 8 and <= 64");
 }
 
-constexpr int kFwdSmem = kTile128 + 4 * kTile64 + kTile128 + 256 + 1024;
-constexpr int kDqSmem = 2 * kTile128 + 4 * kTile64 + kTile128 + 256 + 1024;
-constexpr int kDkvSmem = 2 * kTile128 + 4 * kTile64 + 2 * kTile128 + 1024 + 256 + 1024;
+constexpr int kFwdSmem = kFwdGroups * kFwdGroupBytes + 1024;
+constexpr int kDqSmem = kDqGroups * kDqGroupBytes + 1024;
+constexpr int kDkvSmem = kDkvGroups * kDkvGroupBytes + 1024;
+constexpr int kFwdThreads = 5 * kFwdGroups * 32, kDqThreads = 5 * kDqGroups * 32, kDkvThreads = 5 * kDkvGroups * 32;
 
 void* g_attn_trace = nullptr;
+int g_attn_occupancy[3] = {0, 0, 0};  // resident CTAs per SM reported for fwd / dq / dkv
 
 }  // namespace
 
 void attention_set_trace(void* buf) { g_attn_trace = buf; }
+int attention_occupancy(int which) { return which >= 0 && which < 3 ? g_attn_occupancy[which] : 0; }
 
 void attention_fwd(const AttnDesc& d, cudaStream_t stream) {
   check_shape(d.B, d.T, d.nh, d.hd);
@@ -670,6 +755,24 @@ void attention_fwd(const AttnDesc& d, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     check(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), "cudaFuncSetAttribute(attn_fwd)");
+    // several CTAs per SM are the latency-hiding mechanism of these kernels: ask for the largest shared-memory carve-out
+    check(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout(attn_fwd)");
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_fwd_kernel, kFwdThreads, kFwdSmem);
+    g_attn_occupancy[0] = occ;
+    if (getenv("RB_ATTN_DEBUG") != nullptr) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, attn_fwd_kernel);
+      int o0 = 0, o1 = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, attn_fwd_kernel, kFwdThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, attn_fwd_kernel, kFwdThreads, 32768);
+      int smem_sm = 0, smem_optin = 0, regs_sm = 0;
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, 0);
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0);
+      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, 0);
+      printf("attn_fwd: regs %d static smem %zu maxdyn %d local %zu | occ(dyn=%d)=%d occ(0)=%d occ(32K)=%d | smem/SM %d optin %d regs/SM %d\n",
+             fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, kFwdSmem, occ, o0, o1, smem_sm, smem_optin, regs_sm);
+    }
     configured = true;
   }
   FwdArgs p;
@@ -677,8 +780,9 @@ void attention_fwd(const AttnDesc& d, cudaStream_t stream) {
   p.out = reinterpret_cast<bf16*>(d.out); p.ld_out = d.ld_out; p.lse = d.lse;
   p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
   p.scale_log2 = d.scale * 1.4426950408889634f;
-  dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
-  launch_k(attn_fwd_kernel, grid, kThreads, kFwdSmem, stream, map, p);
+  const long long items = (long long)((d.T + BQ - 1) / BQ) * d.nh * d.B;
+  dim3 grid((unsigned)((items + kFwdGroups - 1) / kFwdGroups));
+  launch_k(attn_fwd_kernel, grid, kFwdThreads, kFwdSmem, stream, map, p);
   RB_CHECK_LAUNCH("attn_fwd_kernel");
 }
 
@@ -691,6 +795,13 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
   if (!configured) {
     check(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem), "cudaFuncSetAttribute(attn_dq)");
     check(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem), "cudaFuncSetAttribute(attn_dkv)");
+    check(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout(attn_dq)");
+    check(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout(attn_dkv)");
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_bwd_dq_kernel, kDqThreads, kDqSmem);
+    g_attn_occupancy[1] = occ;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_bwd_dkv_kernel, kDkvThreads, kDkvSmem);
+    g_attn_occupancy[2] = occ;
     configured = true;
   }
   {
@@ -704,10 +815,10 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
   p.lse = d.lse; p.delta = d.delta; p.dqkv = reinterpret_cast<bf16*>(d.dqkv); p.ld_dqkv = d.ld_dqkv;
   p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
   p.scale = d.scale; p.scale_log2 = d.scale * 1.4426950408889634f;
-  dim3 grid((d.T + BQ - 1) / BQ, d.nh, d.B);
-  launch_k(attn_bwd_dkv_kernel, grid, kThreads, kDkvSmem, stream, map_qkv, map_do, p);
+  const long long items = (long long)((d.T + BQ - 1) / BQ) * d.nh * d.B;
+  launch_k(attn_bwd_dkv_kernel, dim3((unsigned)((items + kDkvGroups - 1) / kDkvGroups)), kDkvThreads, kDkvSmem, stream, map_qkv, map_do, p);
   RB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-  launch_k(attn_bwd_dq_kernel, grid, kThreads, kDqSmem, stream, map_qkv, map_do, p);
+  launch_k(attn_bwd_dq_kernel, dim3((unsigned)((items + kDqGroups - 1) / kDqGroups)), kDqThreads, kDqSmem, stream, map_qkv, map_do, p);
   RB_CHECK_LAUNCH("attn_bwd_dq_kernel");
 }
 

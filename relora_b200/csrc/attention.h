@@ -40,5 +40,7 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream);
 
 // Diagnostics: the heaviest forward CTA writes clock64 stamps (8 x 64 int64) into `buf`; nullptr = off.
 void attention_set_trace(void* buf);
+// resident CTAs per SM of the forward (0), dQ (1) and dK/dV (2) kernels, as reported by the occupancy calculator after first use
+int attention_occupancy(int which);
 
 }  // namespace rb

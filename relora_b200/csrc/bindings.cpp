@@ -492,6 +492,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fp8_quantize_act", &fp8_quantize_act, py::arg("x"), py::arg("x8"), py::arg("inv_scale"), py::arg("amax_cur") = py::none());
   m.def("fp8_prep", &fp8_prep);
   m.def("attention_fwd", &attention_fwd);
+  m.def("attention_occupancy", &rb::attention_occupancy);
   m.def("attention_set_trace", [](const OptTensor& t) {
     if (!t.has_value()) { rb::attention_set_trace(nullptr); return; }
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 8 * 64, "trace buffer: int64 CUDA tensor of >= 512 elements");

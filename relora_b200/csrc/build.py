@@ -34,7 +34,7 @@ HEADERS = ["common.cuh", "sm100.cuh", "gemm.h", "tensormap.h", "fp8out.h", "kern
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + os.environ.get("RB_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DRB_ATTN_GROUPS_FWD=3 for kernel experiments
 
 
 def _cuda_home() -> str:

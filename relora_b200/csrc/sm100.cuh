@@ -82,6 +82,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, but sleeps between polls: for kernels whose waiting warps share issue slots with ALU-bound warps (attention softmax).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 40) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if ((++spins & 0x3fffu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > SM100_WATCHDOG_NS) {
+        printf("sm100 watchdog: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

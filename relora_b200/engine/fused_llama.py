@@ -258,7 +258,7 @@ class FusedLlamaStepper:
         if attention == "native" and not native_ok:
             raise RuntimeError(f"--attention native supports head_dim <= 64 (multiple of 8), got {self.hd}")
         # auto: torch SDPA (cuDNN's sm100 flash kernels) while it is the faster of the two -- measured on B200 (bench/attn_bench.py):
-        # forward 80 vs 48 us, backward 222 vs 137 us at B 24 x T 512 x 16 heads x 48; the tcgen05 kernels are selected with
+        # forward 74 vs 48 us, backward 202 vs 135 us at B 24 x T 512 x 16 heads x 48; the tcgen05 kernels are selected with
         # --attention native (tests/test_kernels_gpu.py::test_attention_fwd_bwd, test_native_attention_matches_sdpa_in_the_executor)
         self.native_attn = attention == "native"
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
