@@ -160,3 +160,35 @@ def test_fp8_frozen_path_tracks_bf16_executor():
     fa.merge_and_reinit()
     l2 = fa.micro_step(ids)
     assert torch.isfinite(l2) and abs(float(l2) - float(la)) < 1.0
+
+
+@pytest.mark.parametrize("extra", [[], ["--frozen_dtype", "fp8", "--attention", "native"]])
+def test_cli_end_to_end_on_the_fused_executor(tmp_path, extra):
+    """torchrun_main on the B200 executor: ReLoRA resets, magnitude pruning, checkpoint layout, autoresume; also with the fp8
+    frozen-weight path and the tcgen05 attention kernels selected from the command line."""
+    import json
+    import os
+
+    from torchrun_main import main
+
+    cfg = {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "vocab_size": 4096, "hidden_size": 256, "intermediate_size": 512,
+           "num_hidden_layers": 2, "num_attention_heads": 4, "rms_norm_eps": 1e-6, "max_sequence_length": 256, "hidden_act": "silu",
+           "bos_token_id": 0, "eos_token_id": 1, "pad_token_id": -1, "initializer_range": 0.02, "use_cache": True}
+    cfg_path = str(tmp_path / "llama_tiny.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    d = str(tmp_path / "run")
+    args = ["--model_config", cfg_path, "--synthetic_data", "4096", "--batch_size", "4", "--total_batch_size", "8", "--max_length", "128",
+            "--lr", "1e-3", "--use_peft", "--lora_r", "128", "--relora", "4", "--cycle_length", "4", "--restart_warmup_steps", "1",
+            "--scheduler", "cosine_restarts", "--warmup_steps", "2", "--num_training_steps", "8", "--save_every", "4",
+            "--eval_every", "100", "--save_dir", d, "--dtype", "bfloat16", "--workers", "0", "--optimizer_magnitude_pruning", "0.9",
+            "--reset_optimizer_on_relora", "false",
+            "--init_lora_a", "kaiming", *extra]
+    res = main(args)
+    assert res["executor"] == "FusedLlamaStepper" and res["update_step"] == 8
+    assert res["n_lora_restarts"] == 1 and res["n_optimizer_resets"] == 1
+    assert torch.isfinite(torch.tensor(res["final_eval_loss"])) and res["final_eval_loss"] < 9.0
+    for f in ("config.json", "pytorch_model.bin", "relora_config.json", "optimizer.pt", "training_state.json"):
+        assert os.path.exists(os.path.join(d, "model_8", f)), f
+    # autoresume picks up the last checkpoint and continues to a longer horizon
+    res2 = main(args + ["--autoresume", "true", "--num_training_steps", "12"])
+    assert res2["update_step"] == 12 and "model_12" in os.listdir(d)
