@@ -206,7 +206,7 @@ def run_ours(args):
             "metric": "training throughput, llama ReLoRA (tokens/s, whole job, device-timed, max over ranks)",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.frozen_dtype != "fp8" else "bf16 (fp8 E4M3 forward GEMMs of the frozen weights)",
+            "dtype": "bf16" if args.frozen_dtype not in ("fp8", "fp8_full") else f"bf16 ({args.frozen_dtype}: fp8 tensor-core GEMMs for the frozen weights)",
             "data": "synthetic token ids, random-init weights", "impl": "ours",
             "config": {"model": args.model, "global_batch": args.batch * args.ga * world, "micro_batch_per_gpu": args.batch,
                        "grad_accumulation": args.ga, "seq_len": args.seq, "lora_r": args.lora_r, "lora_dropout": 0.1,

@@ -142,9 +142,9 @@ def build_parser() -> argparse.ArgumentParser:
     _add_bool(p, "--overlap_comm", True)
     p.add_argument("--attention", type=str, default="auto", choices=["auto", "native", "sdpa"],
                    help="native: tcgen05 flash-attention kernels of this repo (head_dim <= 64); sdpa: torch SDPA (cuDNN)")
-    p.add_argument("--frozen_dtype", type=str, default=None, choices=[None, "bf16", "fp8", "mxfp8", "nvfp4"],
+    p.add_argument("--frozen_dtype", type=str, default=None, choices=[None, "bf16", "fp8", "fp8_full", "mxfp8", "nvfp4"],
                    help="fp8: E4M3 tensor-core path for the frozen weights on the fused executor (per-tensor scales, delayed "
-                        "activation scaling); mxfp8 / nvfp4: block-scaled storage on the module path (alias of --quantize)")
+                        "activation scaling), forward GEMMs only; fp8_full: also the input-gradient GEMMs (E5M2 gradients); mxfp8 / nvfp4: block-scaled storage on the module path (alias of --quantize)")
     p.add_argument("--init_lora_a", type=str, default="zeros", choices=["zeros", "kaiming"],
                    help="zeros reproduces upstream (both LoRA factors zero until the first reset)")
     p.add_argument("--synthetic_data", type=str, default=None,
@@ -190,7 +190,7 @@ def check_args(args: argparse.Namespace, argv: Optional[List[str]] = None) -> ar
     if isinstance(args.tags, str):
         args.tags = args.tags.split(",")
 
-    if args.frozen_dtype not in (None, "bf16", "fp8") and args.quantize is None:  # fp8 is a compute path of the fused executor
+    if args.frozen_dtype not in (None, "bf16", "fp8", "fp8_full") and args.quantize is None:  # fp8 is a compute path of the fused executor
         args.quantize = args.frozen_dtype
 
     if args.relora and not args.use_peft:

@@ -63,7 +63,7 @@ rb::Fp8Out fp8_out(const OptTensor& q8, const OptTensor& inv_scale, const OptTen
 void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N, int64_t K1, const OptTensor& a2, const OptTensor& b2,
           int64_t K2, bool a1_mn, bool b1_mn, int64_t n_per_group, int64_t a1_group_kofs, int64_t a2_group_kofs,
           const OptTensor& residual, double alpha, bool accumulate, int64_t block_n, int64_t split_k, int64_t b1_group_kofs,
-          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias, int64_t cta_pair, bool fp8,
+          bool b1_local_n, int64_t m_per_group, int64_t b1_mn_ofs_per_mgroup, const OptTensor& bias, int64_t cta_pair, int64_t fp8,
           const OptTensor& alpha_dev) {
   c10::cuda::CUDAGuard guard(out.device());
   rb::GemmDesc d;
@@ -76,7 +76,7 @@ void gemm(const Tensor& a1, const Tensor& b1, Tensor& out, int64_t M, int64_t N,
     }
     d.a1.ptr = a1.data_ptr(); d.a1.ld = a1.stride(0); d.a1.mn_major = false;
     d.b1.ptr = b1.data_ptr(); d.b1.ld = b1.stride(0); d.b1.mn_major = false;
-    d.fp8 = true;
+    d.fp8 = true; d.fp8_a_e5m2 = fp8 == 2;
   } else {
     d.a1 = operand(a1, a1_mn, "a1");
     d.b1 = operand(b1, b1_mn, "b1");
@@ -192,28 +192,35 @@ void dropout_combine(const OptTensor& base, const Tensor& parts, Tensor& out, co
                       (uint32_t)llround(p * 65536.0), (float)(1.0 / (1.0 - p)), cur_stream());
 }
 
-void fp8_quantize_weight(const Tensor& w, Tensor& w8, Tensor& scratch, Tensor& scale, Tensor& inv_scale) {
+void fp8_quantize_weight(const Tensor& w, Tensor& w8, Tensor& scratch, Tensor& scale, Tensor& inv_scale, const OptTensor& w8t) {
   chk_bf16(w, "w"); chk_2d_rowmajor(w, "w");
   TORCH_CHECK(w8.is_cuda() && w8.element_size() == 1 && w8.dim() == 2 && w8.stride(1) == 1 && w8.sizes() == w.sizes(), "w8: one-byte tensor shaped like w");
+  void* tp = nullptr;
+  long long tld = 0;
+  if (w8t.has_value()) {
+    TORCH_CHECK(w8t->is_cuda() && w8t->element_size() == 1 && w8t->dim() == 2 && w8t->stride(1) == 1 && w8t->size(0) == w.size(1) && w8t->size(1) == w.size(0),
+                "w8t: one-byte tensor shaped like w transposed");
+    tp = w8t->data_ptr(); tld = w8t->stride(0);
+  }
   c10::cuda::CUDAGuard guard(w.device());
-  rb::fp8_quantize_weight(w.data_ptr(), w.stride(0), w8.data_ptr(), w8.stride(0), (int)w.size(0), (int)w.size(1),
+  rb::fp8_quantize_weight(w.data_ptr(), w.stride(0), w8.data_ptr(), w8.stride(0), tp, tld, (int)w.size(0), (int)w.size(1),
                           const_cast<float*>(f32ptr(scratch)), const_cast<float*>(f32ptr(scale)), const_cast<float*>(f32ptr(inv_scale)),
                           cur_stream());
 }
-void fp8_quantize_act(const Tensor& x, Tensor& x8, const Tensor& inv_scale, const OptTensor& amax_cur) {
+void fp8_quantize_act(const Tensor& x, Tensor& x8, const Tensor& inv_scale, const OptTensor& amax_cur, bool e5m2) {
   chk_bf16(x, "x"); chk_2d_rowmajor(x, "x");
   TORCH_CHECK(x8.is_cuda() && x8.element_size() == 1 && x8.dim() == 2 && x8.stride(1) == 1 && x8.sizes() == x.sizes(), "x8: one-byte tensor shaped like x");
   c10::cuda::CUDAGuard guard(x.device());
   rb::fp8_quantize_act(x.data_ptr(), x.stride(0), x8.data_ptr(), x8.stride(0), (int)x.size(0), (int)x.size(1), f32ptr(inv_scale),
-                       const_cast<float*>(f32ptr(amax_cur)), cur_stream());
+                       const_cast<float*>(f32ptr(amax_cur)), e5m2, cur_stream());
 }
-void fp8_prep(Tensor& state, const Tensor& w_scale, Tensor& inv_sx, Tensor& alpha_main, Tensor& alpha_inv, double margin) {
+void fp8_prep(Tensor& state, const Tensor& w_scale, Tensor& inv_sx, Tensor& alpha_main, Tensor& alpha_inv, double margin, int64_t n_e4m3) {
   const int n = (int)w_scale.numel();
   TORCH_CHECK(state.numel() == 2 * n && inv_sx.numel() == n && alpha_main.numel() == n && alpha_inv.numel() == n, "fp8_prep: size mismatch");
   TORCH_CHECK(state.is_contiguous() && w_scale.is_contiguous() && inv_sx.is_contiguous() && alpha_main.is_contiguous() && alpha_inv.is_contiguous());
   c10::cuda::CUDAGuard guard(state.device());
   rb::fp8_prep(const_cast<float*>(f32ptr(state)), f32ptr(w_scale), const_cast<float*>(f32ptr(inv_sx)), const_cast<float*>(f32ptr(alpha_main)),
-               const_cast<float*>(f32ptr(alpha_inv)), n, (float)margin, cur_stream());
+               const_cast<float*>(f32ptr(alpha_inv)), n, (float)margin, n_e4m3 < 0 ? n : (int)n_e4m3, cur_stream());
 }
 
 // out[M,N] = dy[M,Kb]·W[Kb,N] + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)     (fused input gradient of a stacked LoRA group)
@@ -488,9 +495,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_expand", &dropout_expand, py::arg("x"), py::arg("xd"), py::arg("seed"), py::arg("keys"), py::arg("p"), py::arg("q8") = py::none(),
         py::arg("q_inv_scale") = py::none(), py::arg("q_amax") = py::none());
   m.def("dropout_combine", &dropout_combine);
-  m.def("fp8_quantize_weight", &fp8_quantize_weight);
-  m.def("fp8_quantize_act", &fp8_quantize_act, py::arg("x"), py::arg("x8"), py::arg("inv_scale"), py::arg("amax_cur") = py::none());
-  m.def("fp8_prep", &fp8_prep);
+  m.def("fp8_quantize_weight", &fp8_quantize_weight, py::arg("w"), py::arg("w8"), py::arg("scratch"), py::arg("scale"), py::arg("inv_scale"),
+        py::arg("w8t") = py::none());
+  m.def("fp8_quantize_act", &fp8_quantize_act, py::arg("x"), py::arg("x8"), py::arg("inv_scale"), py::arg("amax_cur") = py::none(), py::arg("e5m2") = false);
+  m.def("fp8_prep", &fp8_prep, py::arg("state"), py::arg("w_scale"), py::arg("inv_sx"), py::arg("alpha_main"), py::arg("alpha_inv"), py::arg("margin"),
+        py::arg("n_e4m3") = -1);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_occupancy", &rb::attention_occupancy);
   m.def("attention_set_trace", [](const OptTensor& t) {

@@ -40,6 +40,7 @@ struct GemmDesc {
   const void* bias = nullptr;      // bf16 [N], added in fp32 (after alpha, before the residual)
   float alpha = 1.0f;
   const float* alpha_dev = nullptr;  // optional device scalar multiplied into alpha
+  bool fp8_a_e5m2 = false;  // with fp8: A1 is E5M2 (gradients), B1 stays E4M3
   bool fp8 = false;  // A1 / B1 hold E4M3 bytes (K-major, leading dimensions in bytes); A2 / B2 (the LoRA branch) stay bf16
   int block_n = 0;  // 0 = auto, else 128 or 256
   int split_k = 1;  // 1 = off, 0 = auto, >1 = fixed (fp32 accumulate outputs only: partial sums via atomics)

@@ -54,7 +54,7 @@ struct KernelArgs {
   const bf16* bias;  // [N], added in fp32 (Pythia projections carry biases)
   float alpha;
   const float* alpha_dev;  // optional device scalar multiplied into alpha (fp8 dequantisation scales live on the device)
-  int fp8;                 // segment 1 (A1, B1) holds E4M3 bytes: k-blocks of 128 elements, kind::f8f6f4 MMAs
+  int fp8;                 // segment 1 (A1, B1) holds fp8 bytes: k-blocks of 128 elements, kind::f8f6f4 MMAs (2: A1 is E5M2)
   int out_f32, accumulate;
   int num_m_tiles, num_n_tiles;
   int tiles_per_group;  // N-tiles per output-column group (the last one of a group may be ragged)
@@ -242,7 +242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     if (lane == 0 && leader) {
       constexpr uint32_t idesc1 = make_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t idesc2 = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
-      constexpr uint32_t idesc8 = make_idesc_e4m3(kTileM, BLOCK_N);
+      const uint32_t idesc8 = p.fp8 == 2 ? make_idesc_e4m3(kTileM, BLOCK_N, 1) : make_idesc_e4m3(kTileM, BLOCK_N, 0);
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_flag) {
         if constexpr (PAIR) umma_f16_ss_pair(d, da, db, idesc, acc_flag);
         else umma_f16_ss(d, da, db, idesc, acc_flag);
@@ -1020,7 +1020,7 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   p.out = d.out; p.ldc = d.ldc; p.residual = reinterpret_cast<const bf16*>(d.residual); p.ldr = d.ldr;
   p.bias = reinterpret_cast<const bf16*>(d.bias);
   if (d.bias != nullptr && d.out_f32) throw std::runtime_error("gemm: bias is only fused for bf16 outputs");
-  p.alpha = d.alpha; p.alpha_dev = d.alpha_dev; p.fp8 = d.fp8 ? 1 : 0; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
+  p.alpha = d.alpha; p.alpha_dev = d.alpha_dev; p.fp8 = d.fp8 ? (d.fp8_a_e5m2 ? 2 : 1) : 0; p.out_f32 = d.out_f32 ? 1 : 0; p.accumulate = d.accumulate ? 1 : 0;
   p.num_m_tiles = ceil_div(d.M, kTileM);
   const int groups = ceil_div(d.N, p.n_per_group);
   // tiles never straddle a group: the last tile of a group may be ragged (its tail columns are computed but not

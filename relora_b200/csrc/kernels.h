@@ -87,13 +87,15 @@ size_t magnitude_quantile_workspace_bytes();
 
 // ---- fp8 (E4M3) quantisation for the frozen-weight tensor-core path (fp8.cu) ---------------------------
 // weights: amax -> scale -> quantise (scale / inv_scale are device scalars)
-void fp8_quantize_weight(const void* w, long long ld, void* w8, long long ld8, int R, int C, float* amax_scratch, float* scale,
-                         float* inv_scale, cudaStream_t s);
+// w8t (optional): E4M3 copy of the transpose [C, R] for the input-gradient GEMM
+void fp8_quantize_weight(const void* w, long long ld, void* w8, long long ld8, void* w8t, long long ld8t, int R, int C,
+                         float* amax_scratch, float* scale, float* inv_scale, cudaStream_t s);
 // activations: x8 = sat_e4m3(x * *inv_scale); |x| amax recorded into *amax_cur (may be null)
 void fp8_quantize_act(const void* x, long long ld, void* x8, long long ld8, int R, int C, const float* inv_scale, float* amax_cur,
-                      cudaStream_t s);
+                      bool e5m2, cudaStream_t s);
 // once per micro-step: rotate the per-site amax state and derive 1/s_x, s_x*s_w and 1/(s_x*s_w)
+// sites [0, n_e4m3) are E4M3 activations, the rest E5M2 gradients
 void fp8_prep(float* state, const float* w_scale, float* inv_sx, float* alpha_main, float* alpha_inv, int n, float margin,
-              cudaStream_t s);
+              int n_e4m3, cudaStream_t s);
 
 }  // namespace rb

@@ -340,8 +340,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // kind::f8f6f4 with E4M3 A / B (format code 0), K-major operands, fp32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
-  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N, int a_e5m2 = 0) {  // A may be E5M2 (format code 1): gradients
+  return (1u << 4) | (uint32_t(a_e5m2) << 7) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), 128-byte swizzle:

@@ -78,7 +78,7 @@ class FusedLlamaStepper:
     def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
                  transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096,
-                 overlap_wgrad: bool = True, attention: str = "auto", fp8: bool = False):
+                 overlap_wgrad: bool = True, attention: str = "auto", fp8: bool = False, fp8_backward: bool = False):
         ok, why = supports(model)
         if not ok:
             raise RuntimeError(why)
@@ -246,13 +246,23 @@ class FusedLlamaStepper:
             u8 = lambda *sh: torch.zeros(*sh, dtype=torch.uint8, device=dev)  # noqa: E731
             self.W8 = [u8(L, 3 * h, h), u8(L, h, h), u8(L, 2 * fp, h), u8(L, h, fp)]  # sites: qkv, o, gate/up, down
             f32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)  # noqa: E731
-            self.w_scale, self.w_inv_scale, self._amax_scratch = f32(L, 4), f32(L, 4), f32(1)
-            self.act_state = f32(L, 4, 2)  # [amax of the previous micro-step, amax being recorded]
-            self.inv_sx, self.alpha_main, self.alpha_inv = f32(L, 4), f32(L, 4), f32(L, 4)
+            # scale bookkeeping, index [direction, layer, site]: direction 0 = forward activations (E4M3), 1 = output gradients
+            # (E5M2) of the same four projection groups
+            self._w_scale2, self._act_state2 = f32(2, L, 4), f32(2, L, 4, 2)
+            self._inv_sx2, self._alpha_main2, self._alpha_inv2 = f32(2, L, 4), f32(2, L, 4), f32(2, L, 4)
+            self.w_scale, self.act_state = self._w_scale2[0], self._act_state2[0]
+            self.inv_sx, self.alpha_main, self.alpha_inv = self._inv_sx2[0], self._alpha_main2[0], self._alpha_inv2[0]
+            self.w_inv_scale, self._amax_scratch = f32(L, 4), f32(1)
+            self.fp8_bwd = bool(fp8_backward) or os.environ.get("RELORA_B200_FP8_BWD", "0") == "1"
+            self._fp8_bwd_calibrated = False
+            # E4M3 copies of the transposed weights: K-major operands of the input-gradient GEMMs dy·W
+            self.W8T = [u8(L, h, 3 * h), u8(L, h, h), u8(L, h, 2 * fp), u8(L, fp, h)] if self.fp8_bwd else None
             self.fp8_margin = float(os.environ.get("RELORA_B200_FP8_MARGIN", "1.5"))
             self._fp8_calibrated = False
             self._quantize_weights()
         self._fp8_calibrating = False
+        if not self.fp8:
+            self.fp8_bwd = False
         attention = os.environ.get("RELORA_B200_ATTENTION", attention)
         native_ok = self.hd % 8 == 0 and self.hd <= 64
         if attention == "native" and not native_ok:
@@ -279,7 +289,8 @@ class FusedLlamaStepper:
         for l in range(self.L):
             for s_i in range(4):
                 self.C.fp8_quantize_weight(stacks[s_i][l], self.W8[s_i][l], self._amax_scratch, self.w_scale[l, s_i:s_i + 1],
-                                           self.w_inv_scale[l, s_i:s_i + 1])
+                                           self.w_inv_scale[l, s_i:s_i + 1], self.W8T[s_i][l] if self.fp8_bwd else None)
+        self._w_scale2[1].copy_(self._w_scale2[0])
 
     def _alloc(self, B: int, T: int):
         dev, h, f, r, L = self.device, self.h, self.fp, self.r, self.L  # f: padded intermediate size
@@ -318,6 +329,8 @@ class FusedLlamaStepper:
         if self.fp8:
             self.x8_h = torch.empty(M, h, dtype=torch.uint8, device=dev)
             self.x8_f = torch.empty(M, f, dtype=torch.uint8, device=dev)
+            if self.fp8_bwd:
+                self.dy8 = {w: torch.empty(M, w, dtype=torch.uint8, device=dev) for w in {h, 3 * h, 2 * f}}
         if self.native_attn:
             self.attn_o = e(L, M, h)
             self.lse = torch.empty(L, B, self.nh, T, dtype=torch.float32, device=dev)
@@ -488,7 +501,15 @@ class FusedLlamaStepper:
             if G * Ng >= self.dx_split_k:
                 # long reductions: the frozen-path product runs on the 256-wide / CTA-pair GEMM (1.3-1.5x the per-FLOP rate of
                 # the 128-wide multi-accumulator tiles), then one light pass adds the masked low-rank terms
-                g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
+                if self.fp8_bwd and site is not None:
+                    # E5M2 copy of the output gradient (delayed scale) x E4M3 copy of Wᵀ on the kind::f8f6f4 path
+                    l_, s_i = site
+                    dy8 = self.dy8[G * Ng]
+                    C.fp8_quantize_act(dy, dy8, self._inv_sx2[1, l_, s_i:s_i + 1], self._act_state2[1, l_, s_i, 1:2], True)
+                if self.fp8_bwd and site is not None and self._fp8_bwd_calibrated:
+                    g(dy8, self.W8T[s_i][l_], base_out, M=M, N=K, K1=G * Ng, fp8=2, alpha_dev=self._alpha_main2[1, l_, s_i:s_i + 1])
+                else:
+                    g(dy, S_W, base_out, M=M, N=K, K1=G * Ng, b1_mn=True)
                 C.lora_dx(None, None, du, S_A, out, sd, ks, pp, base_out)
             else:
                 # one kernel: out = dy·W + Σ_g keep_g ⊙ (du_g·A_g)/(1-p)  (1+G accumulators in tensor memory, masks in the epilogue)
@@ -577,10 +598,13 @@ class FusedLlamaStepper:
         self.labels.view(self.B_, self.T_)[:, :-1].copy_(self.ids[:, 1:])
         self.labels.view(self.B_, self.T_)[:, -1].fill_(-100)
         if self.fp8:  # rotate the activation amax state, derive this micro-step's scales
-            self.C.fp8_prep(self.act_state, self.w_scale, self.inv_sx, self.alpha_main, self.alpha_inv, self.fp8_margin)
+            self.C.fp8_prep(self._act_state2, self._w_scale2, self._inv_sx2, self._alpha_main2, self._alpha_inv2, self.fp8_margin,
+                            4 * self.L)
         self._forward(True)
         self._loss_and_head_backward(True)
         self._backward()
+        if self.fp8_bwd:
+            self._fp8_bwd_calibrated = True  # the first backward ran in bf16 and recorded the gradient amax of every site
         self.C.seed_advance(self.seed)
 
     # ------------------------------------------------------------------ public stepper interface

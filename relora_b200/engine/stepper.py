@@ -127,7 +127,8 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
         if ok:
             return FusedLlamaStepper(model, info, cuda_graphs=getattr(args, "cuda_graphs", True),
                                      attention=getattr(args, "attention", "auto"),
-                                     fp8=getattr(args, "frozen_dtype", None) == "fp8", **kw)
+                                     fp8=getattr(args, "frozen_dtype", None) in ("fp8", "fp8_full"),
+                                     fp8_backward=getattr(args, "frozen_dtype", None) == "fp8_full", **kw)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
     kw["transport"] = "nccl"  # the module path reduces through the process group (NCCL / gloo)

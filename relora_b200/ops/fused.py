@@ -85,13 +85,13 @@ def gemm(
     b1_mn_ofs_per_mgroup: int = 0,
     bias: Optional[torch.Tensor] = None,
     pair: int = -1,
-    fp8: bool = False,
+    fp8: int = 0,
     alpha_dev: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """``out[M,N] = alpha·(a1·b1ᵀ + a2·b2ᵀ) (+ residual) (+ out)`` on the tcgen05 kernel.
 
     ``pair``: -1 auto, 0 single-CTA tiles, 1 CTA pairs (``tcgen05 cta_group::2``, 256x256 tiles; needs ``block_n`` 256).
-    ``fp8``: ``a1`` / ``b1`` hold E4M3 bytes (K-major); ``alpha_dev``: fp32 device scalar multiplied into ``alpha``.
+    ``fp8``: 1 = ``a1`` / ``b1`` hold E4M3 bytes (K-major), 2 = ``a1`` is E5M2 (gradients); ``alpha_dev``: fp32 device scalar multiplied into ``alpha``.
 
     K-major operands are ``[rows, K]`` row-major; with ``a1_mn`` / ``b1_mn`` the tensor is
     ``[K, rows]`` row-major (the natural layout of activations for weight-gradient GEMMs).
@@ -111,7 +111,7 @@ def gemm(
         assert not accumulate
     _C().gemm(a1, b1, out, M, N, K1, a2, b2, K2, a1_mn, b1_mn, n_per_group, a1_group_kofs, a2_group_kofs,
               residual, float(alpha), accumulate, block_n, split_k, b1_group_kofs, b1_local_n, m_per_group,
-              b1_mn_ofs_per_mgroup, bias, pair, fp8, alpha_dev)
+              b1_mn_ofs_per_mgroup, bias, pair, int(fp8), alpha_dev)
     return out
 
 

@@ -128,7 +128,8 @@ def test_native_attention_matches_sdpa_in_the_executor():
         assert _relerr(ga, gb) < 0.1, n
 
 
-def test_fp8_frozen_path_tracks_bf16_executor():
+@pytest.mark.parametrize("backward", [False, True])
+def test_fp8_frozen_path_tracks_bf16_executor(backward, monkeypatch):
     """--frozen_dtype fp8: E4M3 forward GEMMs for the frozen weights (delayed activation scaling) stay close to the bf16
     executor in loss and LoRA gradients, and keep working across an update and a merge."""
     from relora_b200.engine.fused_llama import FusedLlamaStepper
@@ -138,9 +139,11 @@ def test_fp8_frozen_path_tracks_bf16_executor():
     wa = _build(0.1)
     wb = copy.deepcopy(wa)
     ids = torch.randint(0, 4096, (3, 128), device=dev)
-    fa = FusedLlamaStepper(wa, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=True, fp8=True)
+    if backward:  # E5M2 output gradients x E4M3 Wᵀ for the input-gradient GEMMs; lower the two-kernel threshold so the tiny model uses it
+        monkeypatch.setenv("RELORA_B200_DX_SPLIT_K", "512")
+    fa = FusedLlamaStepper(wa, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=True, fp8=True, fp8_backward=backward)
     fb = FusedLlamaStepper(wb, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=False)
-    assert fa.fp8 and not fb.fp8
+    assert fa.fp8 and not fb.fp8 and fa.fp8_bwd == backward
     fused.seed_state.set(dev, 5)
     la = fa.micro_step(ids)   # the capture warm-up has already calibrated the activation scales
     fused.seed_state.set(dev, 5)
@@ -155,7 +158,7 @@ def test_fp8_frozen_path_tracks_bf16_executor():
         if gb.norm() == 0:
             continue
         worst = max(worst, _relerr(ga, gb))
-    assert worst < 0.25, worst
+    assert worst < (0.4 if backward else 0.25), worst
     fa.update()
     fa.merge_and_reinit()
     l2 = fa.micro_step(ids)
