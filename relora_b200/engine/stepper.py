@@ -132,4 +132,13 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
     kw["transport"] = "nccl"  # the module path reduces through the process group (NCCL / gloo)
+    # the fp8 tensor-core path and the tcgen05 attention kernels belong to the fused executor: say so instead of silently
+    # training in bf16 / with SDPA
+    from ..obs import logger
+
+    if getattr(args, "frozen_dtype", None) in ("fp8", "fp8_full"):
+        logger.warning(f"--frozen_dtype {args.frozen_dtype} needs the fused executor (Llama + ReLoRA on CUDA/bf16); "
+                       "the module path runs the frozen weights in the model dtype")
+    if getattr(args, "attention", "auto") == "native":
+        logger.warning("--attention native needs the fused executor; the module path uses torch SDPA")
     return ModuleStepper(model, info, **kw)

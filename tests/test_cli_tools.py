@@ -109,3 +109,18 @@ def test_glue_metrics():
     assert abs(run_glue.glue_metrics("cola", p, l)["matthews_correlation"] - 0.5773502691896258) < 1e-9
     s = run_glue.glue_metrics("stsb", np.array([0.1, 0.4, 0.9]), np.array([0.0, 0.5, 1.0]))
     assert s["spearmanr"] == 1.0 and s["pearson"] > 0.98
+
+
+def test_engine_only_flags_parse_and_do_not_alias_quantize():
+    """--frozen_dtype fp8 / fp8_full are compute paths of the fused executor (not storage quantisation); --attention picks
+    the attention kernels."""
+    from relora_b200.config import parse_args
+
+    base = ["--model_config", "configs/llama_9m.json", "--synthetic_data", "64", "--batch_size", "2", "--total_batch_size", "2",
+            "--num_training_steps", "2", "--device", "cpu"]
+    a = parse_args(base + ["--frozen_dtype", "fp8_full", "--attention", "native"])
+    assert a.frozen_dtype == "fp8_full" and a.quantize is None and a.attention == "native"
+    b = parse_args(base + ["--frozen_dtype", "nvfp4"])
+    assert b.quantize == "nvfp4"
+    c = parse_args(base)
+    assert c.attention == "auto" and c.frozen_dtype is None
