@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--frozen_dtype", default=None)
     a = ap.parse_args()
     info = DistInfo(0, 0, 1, torch.device("cuda", 0), "nccl")
     torch.cuda.set_device(0)
@@ -59,7 +60,7 @@ def main():
         info, model_config=os.path.join(ROOT, "configs", f"{a.model}.json"), batch_size=a.batch, gradient_accumulation=1,
         total_batch_size=a.batch, max_length=a.seq, use_peft=True, lora_r=128, relora=5000, cycle_length=5000,
         scheduler="cosine_restarts", warmup_steps=500, restart_warmup_steps=100, lr=1e-3, num_training_steps=20000,
-        dtype="bfloat16", device="cuda", cuda_graphs=False, engine="fused")
+        dtype="bfloat16", device="cuda", cuda_graphs=False, engine="fused", frozen_dtype=a.frozen_dtype)
     st = eng.stepper
     st.side = None  # serial launch order so kernels map to tags one to one
     C = st.C
@@ -83,17 +84,18 @@ def main():
         if kw.get("m_per_group"):
             G = M // kw["m_per_group"]
         esz_out = out.element_size()
+        e1 = 1.0 if kw.get("fp8") else 2.0  # bytes per element of segment 1
         flops = 2.0 * M * N * (K1 + K2)
         # compulsory bytes: A once, B once (grouped operands: every group's window once), output written (+read if accumulate)
         a_cols = K1 * (G if kw.get("a1_group_kofs") else 1)
-        by = 2.0 * M * a_cols + 2.0 * N * K1 + 2.0 * (M * K2 * (G if kw.get("a2_group_kofs") else 1) + N * K2)
+        by = e1 * M * a_cols + e1 * N * K1 + 2.0 * (M * K2 * (G if kw.get("a2_group_kofs") else 1) + N * K2)
         by += esz_out * M * N * (2 if kw.get("accumulate") else 1)
         if kw.get("residual") is not None:
             by += 2.0 * M * N
         tag = "gemm M%d N%d K%d%s %s%s%s%s%s" % (
             M, N, K1, "+%d" % K2 if K2 else "", "A:mn " if kw.get("a1_mn") else "", "B:mn " if kw.get("b1_mn") else "",
             "G%d " % G if G > 1 else "", "acc32 " if kw.get("accumulate") and out.dtype == torch.float32 else "",
-            "+res" if kw.get("residual") is not None else "")
+            ("+res" if kw.get("residual") is not None else "") + (" fp8" if kw.get("fp8") else ""))
         n0 = C.launch_count()
         r = real_gemm(a1, b1, out, **kw)
         for _ in range(C.launch_count() - n0):

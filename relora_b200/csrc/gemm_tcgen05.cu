@@ -779,6 +779,19 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
       const uint32_t row = m0 + quad * 32 + lane;
       const uint32_t rowmix = row * 0x9E3779B1u;
+      // two-kernel form: this thread's row of the supplied frozen-path product (2 x 128 bytes) is requested *now*, so the
+      // ~1 us global-memory latency is covered by the LoRA MMAs and the mask hashing below instead of stalling every slab
+      uint4 bpre[2][8];
+      if (kb_base == 0) {
+        const bool row_in = (int)row < p.M;
+        const bf16* bp = p.base + (long long)row * p.ld_base + n0;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            bpre[sl][q] = (row_in && n0 + sl * 64 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + sl * 64 + q * 8)
+                                                                         : make_uint4(0, 0, 0, 0);
+      }
       // ---- phase 1: masked sum of the LoRA accumulators, packed to bf16x2 (overlaps the frozen-path MMAs)
       uint32_t cpk[BLOCK_N / 2];
       mbar_wait(&lora_full[ls], ls_phase);
@@ -840,17 +853,11 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
             packed[q] = pack8(f);
           }
         } else {
-          // frozen-path product read back from global memory (this thread's row: 8 x 16 B of one 128-byte line)
-          const bool row_in = (int)row < p.M;
-          const bf16* bp = p.base + (long long)row * p.ld_base + n0 + sl * 64;
-          uint4 bv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            bv[q] = (row_in && n0 + sl * 64 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + q * 8) : make_uint4(0, 0, 0, 0);
+          // frozen-path product (prefetched at the top of the tile)
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float f[8];
-            unpack8(bv[q], f);
+            unpack8(bpre[sl][q], f);
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
               const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
