@@ -792,6 +792,67 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
             bpre[sl][q] = (row_in && n0 + sl * 64 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + sl * 64 + q * 8)
                                                                          : make_uint4(0, 0, 0, 0);
       }
+      if (kb_base == 0) {
+        // ---- two-kernel form, single phase: per 16 columns, all G accumulators are fetched with one TMEM round trip, masked,
+        // added to the prefetched frozen-path product and written straight into the output slab
+        mbar_wait(&lora_full[ls], ls_phase);
+        tc_fence_after();
+        const uint32_t rloc = quad * 32 + lane;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint8_t* slab = stage_base + (slab_counter % L::kSlabs) * L::kSlabBytes;
+          uint8_t* rowp = slab + rloc * 128;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int ch = sl * 4 + c4;
+            uint32_t rr[G][16];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + ch * 16), rr[g]);
+            tmem_ld_wait();
+            if (sl == 1 && c4 == 3) {  // last read of the accumulators: hand them back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(&lora_empty[ls]);
+            }
+            float cf[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cf[i] = 0.f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const uint32_t sg = rowmix ^ seeds[g];
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const uint32_t cp = (uint32_t)(n0 + ch * 16 + i) >> 1;
+                const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
+                if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[g][i]);
+                if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[g][i + 1]);
+              }
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              float f[8];
+              unpack8(bpre[sl][c4 * 2 + h2], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaf(cf[h2 * 8 + i], p.inv_keep, f[i]);
+              const int q = c4 * 2 + h2;
+              *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = pack8(f);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_2d(&map_out, slab, n0 + sl * 64, m0);
+            tma_store_commit();
+            tma_store_wait_read<L::kSlabs - 2>();
+          }
+          ++slab_counter;
+        }
+        if (++ls == kLoraStages) {
+          ls = 0;
+          ls_phase ^= 1;
+        }
+        continue;
+      }
       // ---- phase 1: masked sum of the LoRA accumulators, packed to bf16x2 (overlaps the frozen-path MMAs)
       uint32_t cpk[BLOCK_N / 2];
       mbar_wait(&lora_full[ls], ls_phase);

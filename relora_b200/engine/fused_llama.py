@@ -273,7 +273,10 @@ class FusedLlamaStepper:
         self.native_attn = attention == "native"
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
         self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
-        self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "2048"))  # stacked output width from which dx uses two kernels
+        # stacked output width from which dx uses two kernels (frozen-path GEMM on 256-wide / CTA-pair tiles + a mask-and-add pass).
+        # The pass costs 30-120 us, so it only pays for long reductions: per-group timings in profiles/ROOFLINE.md put the bf16
+        # break-even near 4096; with fp8 input-gradient GEMMs (twice the rate) at 2048.
+        self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "0")) or (2048 if self.fp8_bwd else 4096)
         self._wg_done: Dict[str, torch.cuda.Event] = {}
 
     # ------------------------------------------------------------------ plumbing
