@@ -664,6 +664,11 @@ class FusedLlamaStepper:
         self.ids.copy_(input_ids)
         self.labels.view(B, T)[:, :-1].copy_(self.ids[:, 1:])
         self.labels.view(B, T)[:, -1].fill_(-100)
+        if self.fp8 and not self._fp8_calibrated:
+            # evaluation before the first training step: bootstrap the activation scales exactly like micro_step does
+            self._fp8_calibrate()
+            self.C.fp8_prep(self._act_state2, self._w_scale2, self._inv_sx2, self._alpha_main2, self._alpha_inv2, self.fp8_margin,
+                            4 * self.L)
         self._forward(False)
         self._loss_and_head_backward(False)
         return self.loss_out.clone()
