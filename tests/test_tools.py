@@ -74,3 +74,23 @@ def test_check_dataset_reports_sizes(tmp_path):
     rep = check(p, vocab_size=100)
     assert rep["ok"] and rep["splits"]["train"]["sequences"] == 20 and rep["splits"]["train"]["tokens"] == 160
     assert not check(p, vocab_size=10)["ok"]
+
+
+def test_metrics_summary_of_a_real_cpu_run(tmp_path):
+    """tools.metrics reads the JSONL sink the trainer writes when wandb is off."""
+    from tools.metrics import load, main, series, summarise
+    from torchrun_main import main as train
+
+    d = str(tmp_path / "run")
+    train(["--model_config", os.path.join(ROOT, "configs", "llama_9m.json"), "--synthetic_data", "512", "--batch_size", "2",
+           "--total_batch_size", "2", "--max_length", "16", "--lr", "1e-3", "--scheduler", "cosine", "--warmup_steps", "1",
+           "--num_training_steps", "5", "--save_every", "5", "--eval_every", "100", "--save_dir", d, "--device", "cpu",
+           "--dtype", "float32", "--workers", "0"])
+    rows = load(d)
+    losses = series(rows, "loss")
+    assert len(losses) == 5 and all(v == v for _, v in losses)
+    s = summarise(rows)
+    assert s["logged_steps"] == 5 and s["first_loss"] > 5.0 and s["last_eval_loss"] is not None
+    out = tmp_path / "loss.csv"
+    main([d, "--csv", str(out)])
+    assert out.read_text().splitlines()[0] == "step,loss" and len(out.read_text().splitlines()) == 6
