@@ -2,10 +2,10 @@
 //
 // Same observable behaviour as the reference's `megatron_dataset/helpers.cpp` (golden outputs in
 // tests/test_neox_data.py):
-//   build_sample_idx_int32/int64   GPT sample index: (position in doc_idx, token offset) per sample boundary
-//   build_blending_indices         greedy largest-deficit interleaving of weighted datasets
-//   build_mapping                  BERT-style sentence-span samples (seeded target lengths + Fisher-Yates shuffle)
-//   build_blocks_mapping           REALM-style blocks (title-aware target length, per-epoch block ids)
+//   build_sample_idx_int32/int64   GPT sample index: (position in doc_idx, token offset) per sample boundary   (helpers.cpp:91-259)
+//   build_blending_indices         greedy largest-deficit interleaving of weighted datasets                     (helpers.cpp:34-89)
+//   build_mapping                  BERT-style sentence-span samples (seeded target lengths + Fisher-Yates)      (helpers.cpp:261-511)
+//   build_blocks_mapping           REALM-style blocks (title-aware target length, per-epoch block ids)          (helpers.cpp:513-745)
 // Written as single-pass walkers over growable buffers; ownership passes to numpy through a capsule.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>

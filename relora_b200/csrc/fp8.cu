@@ -1,4 +1,6 @@
 // E4M3 quantisation for the fp8 frozen-weight path (tcgen05 kind::f8f6f4 GEMMs, csrc/gemm_tcgen05.cu).
+// Capability being replaced: the reference's bitsandbytes-quantised frozen weights (peft_pretraining/relora.py:224-236,
+// 277-299, 314-317: NF4 / int8 storage, dequantise -> bf16 matmul); here the frozen GEMMs themselves run in fp8.
 //
 //   weights     : per-tensor scale from the current amax, refreshed at every ReLoRA merge
 //   activations : per-tensor *delayed* scaling: a site quantises with the scale derived from the amax it observed in the

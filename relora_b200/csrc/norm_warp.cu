@@ -1,4 +1,6 @@
 // Warp-per-row RMSNorm forward / backward for H <= 2048 (one 128-bit vector per lane per step, no block barriers).
+// Reference op: LlamaRMSNorm, peft_pretraining/modeling_llama.py:74-91 (normalise in fp32, round to bf16, then multiply by the
+// bf16 weight -- the rounding order is kept); the dropout-expanded copies feed relora.py:321 (nn.Dropout on the LoRA input).
 //
 // forward : y = w * bf16(x * rstd) (+ G dropout-expanded copies for the LoRA down-projections), rstd saved
 // backward: dx = rstd * (g - xhat * mean(g * xhat)) + dx_add,  g = dy * w
