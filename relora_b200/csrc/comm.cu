@@ -208,8 +208,14 @@ __global__ void norm_exchange_kernel(const CommCtx c, const float* __restrict__ 
 __global__ void __launch_bounds__(512) adam_allgather_kernel(const CommCtx c, const PeerPtrs params, void* param_mc, long long chunk_vec,
                                                              const float* __restrict__ gred, bf16* __restrict__ m, bf16* __restrict__ v,
                                                              float lr, float b1, float b2, float eps, float wd, float bc1_inv, float bc2_rsqrt,
-                                                             const float* __restrict__ grad_scale, const float* __restrict__ skip) {
+                                                             const float* __restrict__ grad_scale, const float* __restrict__ skip,
+                                                             const float* __restrict__ step_dev) {
   if (skip != nullptr && *skip != 0.f) return;
+  if (step_dev != nullptr) {
+    const float t = fmaxf(*step_dev, 1.f);
+    bc1_inv = 1.f / (1.f - powf(b1, t));
+    bc2_rsqrt = 1.f / sqrtf(1.f - powf(b2, t));
+  }
   const float gs = *grad_scale;
   const float decay = 1.f - lr * wd, step_size = lr * bc1_inv;
   const long long lo = chunk_vec * c.rank;
@@ -252,7 +258,7 @@ void fused_update(const CommCtx& c, const FusedUpdateArgs& a, uint32_t epoch0, c
   const float bc2_rsqrt = 1.f / sqrtf(1.f - powf(a.beta2, (float)a.step));
   adam_allgather_kernel<<<blocks, 512, 0, s>>>(c, a.param_bufs, a.param_mc, chunk_vec, a.gred, reinterpret_cast<bf16*>(a.exp_avg),
                                                reinterpret_cast<bf16*>(a.exp_avg_sq), a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, bc1_inv,
-                                               bc2_rsqrt, grad_scale, a.skip);
+                                               bc2_rsqrt, grad_scale, a.skip, a.step_dev);
   RB_CHECK_LAUNCH("adam_allgather");
   xgpu_barrier(c, 1, epoch0, s);  // every replica holds the new parameters before the next forward starts
 }

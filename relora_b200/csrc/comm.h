@@ -48,6 +48,7 @@ struct FusedUpdateArgs {
   long long n;              // multiple of 8 * world
   float lr, beta1, beta2, eps, weight_decay;
   int step;
+  const float* step_dev;    // device-resident step count (nullable): replaces `step` in the bias corrections
   float max_norm;           // <= 0: no clipping
   float inv_world;          // gradients are averaged over ranks
   const float* skip;        // device flag (nullable): != 0 -> no update

@@ -72,10 +72,11 @@ void seed_advance(uint32_t* seed, cudaStream_t s);  // *seed = lowbias32(*seed +
 
 // ---- optimizer -----------------------------------------------------------------------------
 // AdamW on flat buffers.  grad may be bf16 or fp32; state bf16 or fp32.  grad_scale / skip are device scalars
-// (may be null => 1 / false).  lr comes from the host (scheduler).
+// (may be null => 1 / false).  lr comes from the host (scheduler).  step_dev (nullable): device-resident step count that
+// replaces `step` in the bias corrections (it only advances on updates that were not NaN-skipped).
 void adamw_flat(void* param, const void* grad, bool grad_f32, void* exp_avg, void* exp_avg_sq, bool state_f32, long long n,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale,
-                float grad_scale_host, const float* skip, cudaStream_t s);
+                float grad_scale_host, const float* skip, const float* step_dev, cudaStream_t s);
 // out[0] += sum(x^2)  (fp32 accumulate; x bf16 or fp32)
 void sumsq(const void* x, bool is_f32, long long n, float* out, cudaStream_t s);
 void random_prune(void* x, bool is_f32, long long n, float ratio, uint32_t seed, long long col_offset, cudaStream_t s);

@@ -25,8 +25,13 @@ template <typename GT, typename ST>
 __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const GT* __restrict__ g, ST* __restrict__ m, ST* __restrict__ v,
                                                     long long n, float lr, float b1, float b2, float eps, float wd, float bc1_inv,
                                                     float bc2_rsqrt, const float* __restrict__ gscale_ptr, float gscale_host,
-                                                    const float* __restrict__ skip_ptr) {
+                                                    const float* __restrict__ skip_ptr, const float* __restrict__ step_dev) {
   if (skip_ptr != nullptr && *skip_ptr != 0.f) return;
+  if (step_dev != nullptr) {  // device-resident step count (advances only on updates that are not skipped)
+    const float t = fmaxf(*step_dev, 1.f);
+    bc1_inv = 1.f / (1.f - powf(b1, t));
+    bc2_rsqrt = 1.f / sqrtf(1.f - powf(b2, t));
+  }
   const float gs = gscale_host * (gscale_ptr ? *gscale_ptr : 1.f);
   const float decay = 1.f - lr * wd;
   const float step_size = lr * bc1_inv;
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const 
 
 void adamw_flat(void* param, const void* grad, bool grad_f32, void* exp_avg, void* exp_avg_sq, bool state_f32, long long n, float lr,
                 float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale, float grad_scale_host,
-                const float* skip, cudaStream_t s) {
+                const float* skip, const float* step_dev, cudaStream_t s) {
   if (n % 8) throw std::runtime_error("adamw: n must be a multiple of 8");
   const float bc1_inv = 1.f / (1.f - powf(beta1, (float)step));
   const float bc2_rsqrt = 1.f / sqrtf(1.f - powf(beta2, (float)step));
@@ -59,7 +64,7 @@ void adamw_flat(void* param, const void* grad, bool grad_f32, void* exp_avg, voi
   bf16* p = (bf16*)param;
 #define LAUNCH(GT, ST)                                                                                                         \
   adamw_kernel<GT, ST><<<grid, 256, 0, s>>>(p, (const GT*)grad, (ST*)exp_avg, (ST*)exp_avg_sq, n, lr, beta1, beta2, eps,       \
-                                            weight_decay, bc1_inv, bc2_rsqrt, grad_scale, grad_scale_host, skip)
+                                            weight_decay, bc1_inv, bc2_rsqrt, grad_scale, grad_scale_host, skip, step_dev)
   if (grad_f32 && state_f32) LAUNCH(float, float);
   else if (grad_f32) LAUNCH(float, bf16);
   else if (state_f32) LAUNCH(bf16, float);

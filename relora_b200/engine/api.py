@@ -49,6 +49,9 @@ class TrainingEngine:
             from ..ops import fused
 
             native = fused.NativeOptim()
+            from ..ops import reference as _ref
+
+            fused.seed_state.set(device, _ref.mix_seed(args.seed, 0x5eed))  # LoRA-dropout stream follows --seed
         self.stepper = make_stepper(self.model, self.info, args, native=native)
         self.optimizer = self.stepper.optimizer
         self.scheduler = get_scheduler(
@@ -92,12 +95,13 @@ class TrainingEngine:
             loss = self.stepper.micro_step(ids[i])
             total = loss.float() if total is None else total + loss.float()
         mean = total / ga
+        self.last_local_loss = mean  # this rank's loss before the cross-rank mean (device scalar; bench.py's validity check)
         skip = torch.isnan(mean).float()
         if dist.is_initialized() and dist.get_world_size() > 1:
             pack = torch.stack([mean, skip])
             dist.all_reduce(pack)
             mean, skip = pack[0] / dist.get_world_size(), pack[1]
-        self.stepper.update(skip=skip)
+        self.last_grad_norm = self.stepper.update(skip=skip).grad_norm
         # the fused / flat optimizers step inside update(); mark the wrapped torch counter so LambdaLR does not warn about order
         self.optimizer._opt_called = True
         self.scheduler.step()

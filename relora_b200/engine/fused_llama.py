@@ -679,12 +679,12 @@ class FusedLlamaStepper:
         world = self.info.world_size
         if self.comm is not None:
             grp = opt.param_groups[0]
-            opt.step_count += 1
-            opt._step_t.add_(1)
+            opt.advance_step(skip)
             norm = self.comm.fused_update(
                 grads_f32=self.store.grads, grad_buf=self.grad_buf, gred=self.gred, param_buf=self.param_buf,
                 exp_avg=opt.exp_avg, exp_avg_sq=opt.exp_avg_sq, n=self.store.numel, lr=grp["lr"], betas=grp["betas"],
-                eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=skip)
+                eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=skip,
+                step_dev=opt._step_t)
             total = norm[0].clone()
             opt.zero_grad()
             if error_if_nonfinite and not bool(torch.isfinite(total)):

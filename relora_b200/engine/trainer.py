@@ -166,6 +166,15 @@ def _build_data(args, info, state_update_step: int):
     return train_loader, eval_loader, None, prep, vocab
 
 
+def _dropout_seed_value(device):
+    """Current value of the device-resident LoRA-dropout counter (None on CPU, where torch's generator is used)."""
+    if device.type != "cuda":
+        return None
+    from ..ops import fused as _f
+
+    return _f.seed_value(device)
+
+
 def run(args) -> dict:
     """Train according to ``args`` (a namespace from :func:`relora_b200.config.parse_args`)."""
     torch.manual_seed(args.seed)
@@ -275,6 +284,7 @@ def run(args) -> dict:
         model.seed = args.seed
 
     _update_step_ckpt = None
+    _resume_dropout_seed = None
     if args.resume_from:
         logger.info(f"Loading model from {args.resume_from}")
         target = model.wrapped_model if isinstance(model, ReLoRaModel) else model
@@ -285,6 +295,7 @@ def run(args) -> dict:
         st.tokens_seen, st.tokens_seen_before = old["tokens_seen"], old["tokens_seen_before"]
         st.n_lora_restarts = old.get("n_lora_restarts", 0)
         st.n_optimizer_resets = old.get("n_optimizer_resets", 0)
+        _resume_dropout_seed = old.get("dropout_seed")
         if isinstance(model, ReLoRaModel):
             model.n_restarts = st.n_lora_restarts
         logger.info(f"Will train for {args.num_training_steps - _update_step_ckpt} update steps")
@@ -321,6 +332,12 @@ def run(args) -> dict:
         from ..ops import fused as _fused
 
         native = _fused.NativeOptim()
+    if device.type == "cuda":
+        # LoRA-dropout stream: base counter derived from --seed (runs with different seeds draw different masks); a resumed run
+        # continues from the counter saved in training_state.json instead of replaying the masks of step 0
+        from ..ops import reference as _ref
+
+        _fused.seed_state.set(device, _resume_dropout_seed if _resume_dropout_seed is not None else _ref.mix_seed(args.seed, 0x5eed))
     stepper = make_stepper(model, info, args, native=native)
     optimizer = stepper.optimizer
     lora_params = stepper.lora_params
@@ -455,6 +472,8 @@ def run(args) -> dict:
             scheduler.step()
         else:
             logger.error(f"Nan detected in loss_info, loss={float(mean_loss)}, skipping update")
+            if device.type == "cuda" and hasattr(optimizer, "rollback_skipped_step"):
+                optimizer.rollback_skipped_step()  # the device-side skip left the moments untouched; undo the optimistic step count
             n_skipped += 1
             if n_skipped > 0.05 * args.num_training_steps:
                 logger.error("More than 5% of batches skipped due to NaNs, stopping training.")
@@ -472,6 +491,7 @@ def run(args) -> dict:
             with phases.phase("save"):
                 ts = asdict(st)
                 ts["update_time"] = update_time
+                ts["dropout_seed"] = _dropout_seed_value(device)
                 ckpt_lib.save_checkpoint(model, optimizer=optimizer, scheduler=scheduler, training_state=ts,
                                          run_config=run_config, save_dir=directory, dtype=args.dtype, rank=rank,
                                          barrier=barrier, run_id=sink.id if sink else None)
@@ -552,8 +572,9 @@ def run(args) -> dict:
     directory = f"{args.save_dir}/model_{st.update_step}"
     if not os.path.exists(directory):
         logger.info(f"Saving model and optimizer to {directory}, update step {st.update_step}")
-        ts = {k: v for k, v in asdict(st).items() if k != "n_optimizer_resets"}
+        ts = asdict(st)  # incl. n_optimizer_resets (upstream drops it from the final checkpoint; the prune RNG is keyed by it)
         ts["update_time"] = update_time
+        ts["dropout_seed"] = _dropout_seed_value(device)
         ckpt_lib.save_checkpoint(model, optimizer=optimizer, scheduler=scheduler, training_state=ts,
                                  run_config=run_config, save_dir=directory, dtype=args.dtype, rank=rank,
                                  barrier=barrier, run_id=sink.id if sink else None)

@@ -327,14 +327,14 @@ class NativeOptim:
     def __init__(self):
         self._ws = {}
 
-    def adamw_flat(self, p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale, skip):
+    def adamw_flat(self, p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale, skip, step_dev=None):
         gs_t, gs_h = (grad_scale, 1.0) if torch.is_tensor(grad_scale) else (None, float(grad_scale))
         if gs_t is not None:
             gs_t = gs_t.reshape(1).float()
         sk = None
         if skip is not None:
             sk = skip.reshape(1).float() if torch.is_tensor(skip) else torch.tensor([float(skip)], device=p.device)
-        _C().adamw_flat(p, g, m, v, lr, b1, b2, eps, wd, step, gs_t, gs_h, sk)
+        _C().adamw_flat(p, g, m, v, lr, b1, b2, eps, wd, step, gs_t, gs_h, sk, None if step_dev is None else step_dev.reshape(1))
 
     def random_prune_(self, seg, ratio, seed, col_offset):
         _C().random_prune(seg, ratio, seed, col_offset)

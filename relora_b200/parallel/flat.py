@@ -252,6 +252,23 @@ class FlatAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False):
         self.store.zero_grads()
 
+    def advance_step(self, skip=None) -> None:
+        """Count one update.  A NaN-skipped update must not advance Adam's step (upstream simply does not call
+        ``optimizer.step()``, torchrun_main.py:813-822): the authoritative counter ``_step_t`` lives on the device, advances by
+        ``1 - skip`` without a host round trip, is what the native kernels derive the bias corrections from and what
+        ``state_dict()`` saves.  ``step_count`` is the host-side mirror (exact after :meth:`rollback_skipped_step`)."""
+        self.step_count += 1
+        if skip is None or not torch.is_tensor(skip):
+            if not skip:
+                self._step_t.add_(1)
+        else:
+            self._step_t.add_(1.0 - skip.reshape(()).to(self._step_t.dtype).clamp(0, 1))
+
+    def rollback_skipped_step(self) -> None:
+        """Host mirror of a skipped update (the trainer calls this after its host-side NaN check)."""
+        if self.step_count > 0:
+            self.step_count -= 1
+
     # ------------------------------------------------------------------ update
     @torch.no_grad()
     def step(self, closure=None, *, grad_scale=1.0, skip=None, grads=None):
@@ -260,11 +277,11 @@ class FlatAdamW(torch.optim.Optimizer):
         lo, hi = self.shard
         p = self.store.params[lo:hi]
         g = (self.store.grads if grads is None else grads)[lo:hi]
-        if self._native is not None and p.is_cuda:
-            self.step_count += 1  # the device-side skip keeps the moments untouched; the counter drift
-            self._step_t.add_(1)  # of a skipped step only perturbs bias correction, like upstream's
+        if self._native is not None and p.is_cuda and p.dtype == torch.bfloat16 and self.exp_avg.dtype == torch.bfloat16:
+            # the native kernel is the bf16-parameter / bf16-moment AdamW; other dtypes (--dtype float32) take the PyTorch path below
+            self.advance_step(skip)
             self._native.adamw_flat(p, g, self.exp_avg, self.exp_avg_sq, float(lr), b1, b2, eps, wd,
-                                    self.step_count, grad_scale, skip)
+                                    self.step_count, grad_scale, skip, self._step_t)
             return None
         if skip is not None and bool(skip):
             return None
@@ -299,7 +316,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 seg = bufs[key][a - lo : b - lo]
                 if kind == "random":
                     s = ref.mix_seed(seed, reset_index, t_idx, k_idx)
-                    if self._native is not None and seg.is_cuda:
+                    if self._native is not None and seg.is_cuda and seg.dtype == torch.bfloat16:
                         self._native.random_prune_(seg, ratio, s, a - o)
                     else:
                         keep = ref.random_prune_keep_mask(s, b - a, ratio, device=seg.device, offset=a - o)
@@ -317,7 +334,7 @@ class FlatAdamW(torch.optim.Optimizer):
                         from ..relora.optim_reset import magnitude_pruning_
 
                         magnitude_pruning_(self.store.view_like(bufs[key], p, base=lo), ratio)
-                    elif self._native is not None and seg.is_cuda:
+                    elif self._native is not None and seg.is_cuda and seg.dtype == torch.bfloat16:
                         self._native.magnitude_prune_(seg, ratio)
                     else:
                         from ..relora.optim_reset import magnitude_pruning_

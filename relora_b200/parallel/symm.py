@@ -125,10 +125,12 @@ class SymmComm:
 
     def fused_update(self, *, grads_f32: torch.Tensor, grad_buf: SymmBuffer, gred: torch.Tensor, param_buf: SymmBuffer,
                      exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, n: int, lr: float, betas: Tuple[float, float], eps: float,
-                     weight_decay: float, step: int, max_norm: float, skip: Optional[torch.Tensor]) -> torch.Tensor:
+                     weight_decay: float, step: int, max_norm: float, skip: Optional[torch.Tensor],
+                     step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
         sk = None if skip is None else skip.reshape(1).float()
         self.C.comm_fused_update(self.flags.ptrs, self.rank, self.world, self.local_go, grads_f32, grad_buf.ptrs,
                                  grad_buf.mc_ptr(self.use_multicast), gred, param_buf.ptrs, param_buf.mc_ptr(self.use_multicast),
                                  exp_avg, exp_avg_sq, n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
-                                 int(step), float(max_norm), sk, self.norm_out, self.scratch, self._next_epoch(), self.max_blocks)
+                                 int(step), float(max_norm), sk, self.norm_out, self.scratch, self._next_epoch(), self.max_blocks,
+                                 None if step_dev is None else step_dev.reshape(1).float())
         return self.norm_out

@@ -173,7 +173,14 @@ def get_scheduler(
         restart_warmup_steps=restart_warmup_steps,
         adjust_step=adjust_step,
     )
-    return LambdaLR(optimizer, mult, last_epoch)
+    def lr_lambda(step: int) -> float:
+        # a plain function: LambdaLR.state_dict() serialises the __dict__ of callable *objects* and load_state_dict() would
+        # overwrite the freshly built schedule with the checkpoint's (total, warmup, restart_every ...) on resume; like the
+        # reference's functools.partial, only last_epoch / base_lrs are restored and new CLI values win
+        return mult(step)
+
+    lr_lambda.multiplier = mult  # introspection (tools/plot_lr.py, tests)
+    return LambdaLR(optimizer, lr_lambda, last_epoch)
 
 
 # the reference spells it this way (training_utils.py:56); keep the alias for drop-in use
