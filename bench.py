@@ -167,10 +167,15 @@ def timed(fn_step, steps, world, device):
 
 
 def make_tokens(steps, ga, batch, seq, vocab, rank, pinned):
+    """Synthetic ids uniform over the *real* vocabulary [0, vocab - 1): the configs' ``pad_token_id = -1`` makes row vocab - 1 the
+    embedding's padding row (all zeros, never trained; ``modeling_llama.py:433-436``) and real text never contains that id.
+    A sequence that *starts* with it keeps an exactly-zero residual row through every layer (v = 0, no biases, LoRA B = 0), where
+    RMSNorm's backward has gain 1/sqrt(eps) = 1000 per norm; the gradient overflows after ~17 layers.  That is what turned both arms
+    non-finite at 4 and 8 GPUs in round 1 (P = 1/32100 per sequence: ~55 % of 45-step runs at N = 4); see DESIGN.md "root cause"."""
     import torch
 
     g = torch.Generator().manual_seed(1234 + rank)
-    t = torch.randint(0, vocab, (steps, ga, batch, seq), generator=g, dtype=torch.long)
+    t = torch.randint(0, vocab - 1, (steps, ga, batch, seq), generator=g, dtype=torch.long)
     return t.pin_memory() if pinned else t
 
 
@@ -327,7 +332,7 @@ def run_ours(args):
             "metric": METRIC, "value": head["value"], "unit": "tokens/s", "n_gpus": world, "steps": head["steps"], "warmup": head["warmup"],
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.frozen_dtype not in ("fp8", "fp8_full") else f"bf16 ({args.frozen_dtype}: fp8 tensor-core GEMMs for the frozen weights)",
-            "data": "synthetic token ids, random-init weights", "impl": "ours", "config": head["config"],
+            "data": "synthetic token ids (uniform over the vocabulary without the padding row), random-init weights", "impl": "ours", "config": head["config"],
             "impl_details": head["impl_details"], "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
             "valid": valid, "final_loss": head["final_loss"], "final_grad_norm": head["final_grad_norm"],
             "native_so": native.so_path(),
@@ -471,7 +476,7 @@ def run_reference(args):
         out = {
             "metric": METRIC, "value": head["value"], "unit": "tokens/s", "n_gpus": world, "steps": head["steps"], "warmup": head["warmup"],
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic token ids, random-init weights", "impl": "reference", "config": head["config"],
+            "dtype": "bf16", "data": "synthetic token ids (uniform over the vocabulary without the padding row), random-init weights", "impl": "reference", "config": head["config"],
             "impl_details": head["impl_details"], "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": 0, "valid": valid,
         }
         for k in ("nonfinite_at_step", "failed"):

@@ -136,7 +136,6 @@ def _pinpoint(st, toks, w):
 
     from relora_b200.ops import fused
 
-    st.use_graphs, st.side = False, None
     found = {}
 
     def nonfinite(t):
@@ -177,17 +176,29 @@ def _pinpoint(st, toks, w):
             return wrap("C." + k, v) if callable(v) else v
 
     state = {"micro": 0, "calls": 0}
+    # phase 1 (fast, captured graph): which micro-batch turns the accumulated gradients non-finite?
+    bad_i = None
+    for i in range(toks.shape[0]):
+        loss = st.micro_step(toks[i])
+        nfg = nonfinite(st.store.grads)
+        w({"scan_micro": i, "loss": float(loss), "grad_nonfinite": nfg})
+        if nfg:
+            bad_i = i
+            break
+    if bad_i is None:
+        w({"culprit": None, "note": "no micro-batch of this update produced non-finite gradients"})
+        return
+    # phase 2: replay that micro-batch eagerly (no graph, no side stream) with every kernel call checked
+    st.store.grads.zero_()
+    st.use_graphs, st.side = False, None
     real_C, real_gemm, real_grad = st.C, fused.gemm, torch.autograd.grad
     st.C = Proxy(real_C)
     fused.gemm = wrap("gemm", real_gemm)
     torch.autograd.grad = wrap("sdpa_backward(autograd.grad)", real_grad)
     try:
-        for i in range(toks.shape[0]):
-            state["micro"], state["calls"] = i, 0
-            loss = st.micro_step(toks[i])
-            w({"pinpoint_micro": i, "loss": float(loss), "grad_nonfinite": nonfinite(st.store.grads), "culprit": found.get("name")})
-            if found:
-                break
+        state["micro"], state["calls"] = bad_i, 0
+        loss = st.micro_step(toks[bad_i])
+        w({"pinpoint_micro": bad_i, "loss": float(loss), "grad_nonfinite": nonfinite(st.store.grads), "culprit": found.get("name")})
     finally:
         st.C, fused.gemm, torch.autograd.grad = real_C, real_gemm, real_grad
     if found:

@@ -352,6 +352,16 @@ void embedding_bwd(const Tensor& ids, const Tensor& dout, Tensor& dtable, int64_
                     cur_stream());
 }
 
+void embedding_bwd_sorted(const Tensor& sorted_ids, const Tensor& perm, const Tensor& dout, Tensor& dtable, int64_t padding_idx) {
+  chk_bf16(dout, "dout");
+  TORCH_CHECK(dtable.scalar_type() == at::kFloat && dtable.is_contiguous() && dout.is_contiguous());
+  TORCH_CHECK(sorted_ids.scalar_type() == at::kLong && perm.scalar_type() == at::kLong && sorted_ids.is_contiguous() && perm.is_contiguous() &&
+              sorted_ids.numel() == perm.numel());
+  c10::cuda::CUDAGuard guard(dout.device());
+  rb::embedding_bwd_sorted(sorted_ids.data_ptr<int64_t>(), perm.data_ptr<int64_t>(), dout.data_ptr(), dtable.data_ptr<float>(),
+                           (int)sorted_ids.numel(), (int)dtable.size(1), padding_idx, cur_stream());
+}
+
 void cross_entropy_fwd_bwd(Tensor& logits, const Tensor& labels, int64_t V, double grad_scale, int64_t ignore_index, Tensor& loss_sum,
                            Tensor& count) {
   chk_bf16(logits, "logits"); chk_2d_rowmajor(logits, "logits");
@@ -451,19 +461,20 @@ void comm_allreduce_bf16(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t w
   rb::allreduce_bf16(comm_ctx(flag_ptrs, rank, world, local_go), peer_ptrs(buf_ptrs), reinterpret_cast<void*>(mc_ptr), off_elems, n,
                      (uint32_t)epoch, (int)max_blocks, cur_stream());
 }
-void comm_fused_update(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, Tensor& local_go, const Tensor& grads_f32,
+void comm_fused_update(std::vector<int64_t> flag_ptrs, int64_t rank, int64_t world, Tensor& local_go, const OptTensor& grads_f32,
                        std::vector<int64_t> grad_ptrs, int64_t grad_mc, Tensor& gred, std::vector<int64_t> param_ptrs, int64_t param_mc,
                        Tensor& exp_avg, Tensor& exp_avg_sq, int64_t n, double lr, double b1, double b2, double eps, double wd, int64_t step,
                        double max_norm, const OptTensor& skip, Tensor& norm_out, Tensor& scratch, int64_t epoch, int64_t max_blocks,
                        const OptTensor& step_dev) {
-  TORCH_CHECK(grads_f32.scalar_type() == at::kFloat && grads_f32.is_contiguous() && grads_f32.numel() >= n, "grads must be fp32 [n]");
+  if (grads_f32.has_value())
+    TORCH_CHECK(grads_f32->scalar_type() == at::kFloat && grads_f32->is_contiguous() && grads_f32->numel() >= n, "grads must be fp32 [n]");
   TORCH_CHECK(gred.scalar_type() == at::kFloat && gred.numel() * world >= n, "gred must be fp32 [n / world]");
   chk_bf16(exp_avg, "exp_avg"); chk_bf16(exp_avg_sq, "exp_avg_sq");
   TORCH_CHECK(exp_avg.numel() * world >= n && exp_avg_sq.numel() * world >= n, "moments must be [n / world]");
   TORCH_CHECK(norm_out.scalar_type() == at::kFloat && scratch.scalar_type() == at::kFloat && scratch.numel() >= 2);
   c10::cuda::CUDAGuard guard(local_go.device());
   rb::FusedUpdateArgs a;
-  a.grads_f32 = grads_f32.data_ptr<float>();
+  a.grads_f32 = grads_f32.has_value() ? grads_f32->data_ptr<float>() : nullptr;
   a.grad_bufs = peer_ptrs(grad_ptrs); a.grad_mc = reinterpret_cast<void*>(grad_mc);
   a.gred = gred.data_ptr<float>();
   a.param_bufs = peer_ptrs(param_ptrs); a.param_mc = reinterpret_cast<void*>(param_mc);
@@ -518,6 +529,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd", &embedding_bwd);
+  m.def("embedding_bwd_sorted", &embedding_bwd_sorted);
   m.def("cross_entropy_fwd_bwd", &cross_entropy_fwd_bwd);
   m.def("transpose", &transpose);
   m.def("add", &add);

@@ -200,7 +200,8 @@ __global__ void norm_exchange_kernel(const CommCtx c, const float* __restrict__ 
     const float norm = sqrtf(tot) * inv_world;  // norm of the rank-averaged gradient
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
-    *grad_scale = coef * inv_world;
+    // a non-finite gradient norm poisons the scale on purpose: the Adam stage skips the update (see adam_allgather_kernel)
+    *grad_scale = (norm < INFINITY) ? coef * inv_world : __int_as_float(0x7fc00000);
     *norm_out = norm;
   }
 }
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(512) adam_allgather_kernel(const CommCtx c, co
     bc2_rsqrt = 1.f / sqrtf(1.f - powf(b2, t));
   }
   const float gs = *grad_scale;
+  if (!(fabsf(gs) < INFINITY)) return;  // non-finite gradient norm: leave parameters and moments untouched on every rank
   const float decay = 1.f - lr * wd, step_size = lr * bc1_inv;
   const long long lo = chunk_vec * c.rank;
   const uint4* plocal = reinterpret_cast<const uint4*>(params.ptr[c.rank]);
@@ -245,9 +247,11 @@ void fused_update(const CommCtx& c, const FusedUpdateArgs& a, uint32_t epoch0, c
   const long long n_vec = a.n / 8, chunk_vec = n_vec / c.world;
   const int blocks = std::max(1, std::min<int>(a.max_blocks, (int)((chunk_vec + 511) / 512)));
   check(cudaMemsetAsync(a.sq_accum, 0, sizeof(float), s), "memset(sq_accum)");
-  const int cast_blocks = (int)std::min<long long>((n_vec + 511) / 512, (long long)num_sms() * 4);
-  cast_to_symm_kernel<<<cast_blocks, 512, 0, s>>>(a.grads_f32, reinterpret_cast<bf16*>(a.grad_bufs.ptr[c.rank]), n_vec);
-  RB_CHECK_LAUNCH("cast_to_symm");
+  if (a.grads_f32 != nullptr) {  // null: the bf16 gradients already live in the symmetric buffer (module path: .grad views)
+    const int cast_blocks = (int)std::min<long long>((n_vec + 511) / 512, (long long)num_sms() * 4);
+    cast_to_symm_kernel<<<cast_blocks, 512, 0, s>>>(a.grads_f32, reinterpret_cast<bf16*>(a.grad_bufs.ptr[c.rank]), n_vec);
+    RB_CHECK_LAUNCH("cast_to_symm");
+  }
   xgpu_barrier(c, 0, epoch0, s);  // every rank's bf16 gradients are in place
   reduce_scatter_kernel<<<blocks, 512, 0, s>>>(c, a.grad_bufs, a.grad_mc, chunk_vec, a.gred, a.sq_accum);
   RB_CHECK_LAUNCH("reduce_scatter");

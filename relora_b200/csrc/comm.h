@@ -37,7 +37,7 @@ void allreduce_bf16(const CommCtx& c, const PeerPtrs& bufs, void* mc, long long 
 //   4. AdamW on chunk r (moments are chunk-sized, local) and broadcast of the updated bf16 parameters to every peer
 //   5. barrier
 struct FusedUpdateArgs {
-  const float* grads_f32;   // local [n]
+  const float* grads_f32;   // local [n]; nullptr: the bf16 gradients are already in grad_bufs[rank]
   PeerPtrs grad_bufs;       // symmetric bf16 [n]
   void* grad_mc;            // multicast alias or nullptr
   float* gred;              // local fp32 [n / world]

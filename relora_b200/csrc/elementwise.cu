@@ -405,6 +405,43 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __res
     for (int j = 0; j < 8; ++j) atomicAdd(dst + j, f[j]);
   }
 }
+// Deterministic variant: `sorted_ids` / `perm` are the token ids in ascending order (stable) and the positions they came from.
+// One block per sorted position; only the first position of every run of equal ids works: it adds the rows of that token's
+// occurrences in position order (fixed summation order) and is the only writer of its table row -- no atomics, so the result
+// is bit-identical from run to run and across ranks (torch's dense embedding backward is atomic, too).
+__global__ void __launch_bounds__(128) embedding_bwd_sorted_kernel(const int64_t* __restrict__ sorted_ids, const int64_t* __restrict__ perm,
+                                                                   const bf16* __restrict__ dout, float* __restrict__ dtable, int M, int hv,
+                                                                   long long padding_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = blockIdx.x;
+  const long long id = sorted_ids[i];
+  if (id == padding_idx || (i > 0 && sorted_ids[i - 1] == id)) return;
+  for (int c = threadIdx.x; c < hv; c += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = i; k < M && sorted_ids[k] == id; ++k) {
+      float f[8];
+      unpack8(reinterpret_cast<const bf16x8*>(dout)[perm[k] * hv + c], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float4* dst = reinterpret_cast<float4*>(dtable + (id * hv + c) * 8);
+    float4 a = dst[0], b = dst[1];
+    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
+    b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+void embedding_bwd_sorted(const int64_t* sorted_ids, const int64_t* perm, const void* dout, float* dtable, int M, int H,
+                          long long padding_idx, cudaStream_t s) {
+  if (H % 8) throw std::runtime_error("embedding: H must be a multiple of 8");
+  if (M <= 0) return;
+  launch_k(embedding_bwd_sorted_kernel, M, 128, 0, s, sorted_ids, perm, (const bf16*)dout, dtable, M, H / 8, padding_idx);
+  RB_CHECK_LAUNCH("embedding_bwd_sorted");
+}
 void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int H, cudaStream_t s) {
   if (H % 8) throw std::runtime_error("embedding: H must be a multiple of 8");
   const long long total = (long long)M * (H / 8);

@@ -56,6 +56,9 @@ void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, 
 void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int H, cudaStream_t s);
 // dtable_f32[ids[m], :] += dout[m, :]   (skips padding_idx)
 void embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int M, int H, long long padding_idx, cudaStream_t s);
+// deterministic: ids sorted ascending (stable) with their source positions; one writer per table row, fixed summation order
+void embedding_bwd_sorted(const int64_t* sorted_ids, const int64_t* perm, const void* dout, float* dtable, int M, int H,
+                          long long padding_idx, cudaStream_t s);
 
 // ---- loss ----------------------------------------------------------------------------------
 // Row-wise softmax cross-entropy over logits [M, ld] (V valid columns), in place:

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const 
     bc2_rsqrt = 1.f / sqrtf(1.f - powf(b2, t));
   }
   const float gs = gscale_host * (gscale_ptr ? *gscale_ptr : 1.f);
+  if (!(fabsf(gs) < INFINITY)) return;  // non-finite gradient norm (the scale is poisoned by the caller): skip the update
   const float decay = 1.f - lr * wd;
   const float step_size = lr * bc1_inv;
   const long long nv = n / 8;

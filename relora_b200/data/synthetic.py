@@ -17,6 +17,10 @@ __all__ = ["SyntheticTokens", "write_synthetic_hf_dataset"]
 
 
 class SyntheticTokens(Dataset):
+    """Ids are uniform over ``[0, vocab_size - 1)``: the last row is the embedding's padding row under the reference configs
+    (``pad_token_id = -1``), which real tokenised text never contains -- and a sequence *starting* with it keeps an all-zero
+    residual row whose RMSNorm backward (gain 1/sqrt(eps) per norm) overflows in deep models (bench.py:make_tokens)."""
+
     def __init__(self, n_sequences: int, seq_len: int, vocab_size: int, seed: int = 0):
         self.n, self.seq_len, self.vocab_size, self.seed = n_sequences, seq_len, vocab_size, seed
 
@@ -26,7 +30,7 @@ class SyntheticTokens(Dataset):
     def __getitem__(self, i: int):
         g = torch.Generator()
         g.manual_seed((self.seed * 0x9E3779B1 + int(i) * 0x85EBCA77 + 12345) & 0x7FFFFFFFFFFFFFFF)
-        return {"input_ids": torch.randint(0, self.vocab_size, (self.seq_len,), generator=g, dtype=torch.long)}
+        return {"input_ids": torch.randint(0, max(1, self.vocab_size - 1), (self.seq_len,), generator=g, dtype=torch.long)}
 
     def shard(self, rank: int, world_size: int) -> "SyntheticTokens":
         """Contiguous shard, like ``split_dataset_by_node``."""
@@ -53,8 +57,8 @@ def write_synthetic_hf_dataset(path: str, n_train: int, n_val: int, seq_len: int
     import datasets
 
     g = torch.Generator().manual_seed(seed)
-    train = torch.randint(0, vocab_size, (n_train, seq_len), generator=g).tolist()
-    val = torch.randint(0, vocab_size, (n_val, seq_len), generator=g).tolist()
+    train = torch.randint(0, max(1, vocab_size - 1), (n_train, seq_len), generator=g).tolist()
+    val = torch.randint(0, max(1, vocab_size - 1), (n_val, seq_len), generator=g).tolist()
     dd = datasets.DatasetDict({
         "train": datasets.Dataset.from_dict({"input_ids": train}),
         "validation": datasets.Dataset.from_dict({"input_ids": val}),

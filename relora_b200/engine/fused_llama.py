@@ -278,6 +278,8 @@ class FusedLlamaStepper:
         # break-even near 4096; with fp8 input-gradient GEMMs (twice the rate) at 2048.
         self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "0")) or (2048 if self.fp8_bwd else 4096)
         self._wg_done: Dict[str, torch.cuda.Event] = {}
+        # embedding backward without atomics (default); RELORA_B200_ATOMIC_EMBEDDING=1 selects the atomicAdd scatter
+        self.deterministic_embedding = os.environ.get("RELORA_B200_ATOMIC_EMBEDDING", "0") != "1"
 
     # ------------------------------------------------------------------ plumbing
     @staticmethod
@@ -581,7 +583,12 @@ class FusedLlamaStepper:
             self._join("d")  # this layer's down_proj weight gradients read the buffer written next
             C.rmsnorm_bwd(self.dxn2, self.x_in[l], S.w1, self.rstd1[l], dx, dx_other, S.gw1, ws, tk)
             dx, dx_other = dx_other, dx
-        C.embedding_bwd(self.ids.view(-1), dx, self.gW_emb, self.pad_idx)
+        if self.deterministic_embedding:
+            # stable sort of the token ids (12 K keys) -> one writer per table row, fixed summation order: bit-reproducible
+            sorted_ids, perm = torch.sort(self.ids.view(-1), stable=True)
+            C.embedding_bwd_sorted(sorted_ids, perm, dx, self.gW_emb, self.pad_idx)
+        else:
+            C.embedding_bwd(self.ids.view(-1), dx, self.gW_emb, self.pad_idx)
         for tag in ("d", "gu", "o", "qkv"):
             self._join(tag)
         self._attn_saved.clear()
@@ -686,6 +693,7 @@ class FusedLlamaStepper:
                 eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=skip,
                 step_dev=opt._step_t)
             total = norm[0].clone()
+            opt.undo_step_if_nonfinite(total, skip)
             opt.zero_grad()
             if error_if_nonfinite and not bool(torch.isfinite(total)):
                 raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
@@ -702,6 +710,7 @@ class FusedLlamaStepper:
             self.C.sumsq(grads, sq)
             total = sq[0].sqrt() / world
             coef = torch.clamp(self.clip / (total + 1e-6), max=1.0) if self.clip and self.clip > 0 else torch.ones_like(total)
+            coef = torch.where(torch.isfinite(total), coef, torch.full_like(coef, float("nan")))  # non-finite norm: skip the update
             scale = coef / world
         else:
             self.sync.reduce()

@@ -58,11 +58,40 @@ class ModuleStepper:
         self.clip = clip_grad_norm
         broadcast_params(model)
         named = trainable_named_parameters(model)
-        allocator = symm_factory.allocator() if (symm_factory is not None and transport == "p2p") else None
-        self.store = FlatParamStore(named, world_size=info.world_size, allocator=allocator)
-        symm = symm_factory.bind(self.store) if (symm_factory is not None and transport == "p2p") else None
-        self.sync = GradSync(self.store, info, transport=transport, zero=zero, symm=symm)
-        shard = self.sync.shard if zero else None
+        # ---- transport: the hand-written NVLink update (csrc/comm.cu) when symmetric memory is available -- bf16 parameters on
+        # CUDA, more than one rank -- and NCCL / gloo otherwise.  Same kernel chain as the fused executor, except that the bf16
+        # gradients autograd accumulated are already in the symmetric buffer (no cast pass).
+        self.comm = None
+        p0 = named[0][1]
+        if info.world_size > 1 and transport in ("p2p", "auto") and p0.is_cuda and p0.dtype == torch.bfloat16:
+            from ..parallel.symm import SymmComm, symmetric_memory_available
+
+            if symmetric_memory_available():
+                try:
+                    self.comm = SymmComm()
+                except Exception as e:  # no P2P access, allocation failure, ...
+                    if transport == "p2p":
+                        raise
+                    from ..obs import logger
+
+                    logger.warning(f"peer-memory collectives unavailable ({type(e).__name__}: {e}); using NCCL")
+            elif transport == "p2p":
+                raise RuntimeError("--comm p2p needs torch symmetric memory over an NCCL process group")
+        elif transport == "p2p" and info.world_size > 1:
+            raise RuntimeError("--comm p2p needs bf16 parameters on CUDA")
+        if self.comm is not None:
+            alloc = self.comm.allocator()
+            self.store = FlatParamStore(named, world_size=info.world_size, allocator=alloc, grad_allocator=alloc)
+            self.sync = GradSync(self.store, info, transport="nccl", zero=False)
+            self.sync.transport = "p2p"
+            self.param_buf = self.comm.buffer_of(self.store.params)
+            self.grad_buf = self.comm.buffer_of(self.store.grads)
+            self.gred = torch.empty(self.store.numel // info.world_size, dtype=torch.float32, device=p0.device)
+            shard = self.store.shard_bounds(info.rank, info.world_size)  # ZeRO-1 dataflow: each rank owns 1/world of the moments
+        else:
+            self.store = FlatParamStore(named, world_size=info.world_size)
+            self.sync = GradSync(self.store, info, transport="nccl", zero=zero)
+            shard = self.sync.shard if zero else None
         self.optimizer = FlatAdamW(self.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                    shard=shard, native=native)
         self.trainable_params = [p for _, p in named]
@@ -87,6 +116,23 @@ class ModuleStepper:
     # ------------------------------------------------------------------ one optimizer update
     @torch.no_grad()
     def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
+        if self.comm is not None:
+            opt = self.optimizer
+            grp = opt.param_groups[0]
+            sk = None if skip is None else (skip if torch.is_tensor(skip) else torch.tensor(float(skip), device=self.store.device))
+            opt.advance_step(sk)
+            norm = self.comm.fused_update(
+                grads_f32=None, grad_buf=self.grad_buf, gred=self.gred, param_buf=self.param_buf, exp_avg=opt.exp_avg,
+                exp_avg_sq=opt.exp_avg_sq, n=self.store.numel, lr=grp["lr"], betas=grp["betas"], eps=grp["eps"],
+                weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=sk, step_dev=opt._step_t)
+            total = norm[0].clone()
+            opt.undo_step_if_nonfinite(total, sk)
+            opt.zero_grad()
+            if error_if_nonfinite and not bool(torch.isfinite(total)):
+                raise RuntimeError(
+                    f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped."
+                )
+            return UpdateInfo(total, False)
         self.sync.reduce()
         total, scale = self.sync.grad_norm_and_scale(self.clip)
         if error_if_nonfinite and not bool(torch.isfinite(total)):
@@ -131,7 +177,8 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
                                      fp8_backward=getattr(args, "frozen_dtype", None) == "fp8_full", **kw)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
-    kw["transport"] = "nccl"  # the module path reduces through the process group (NCCL / gloo)
+    if info.device.type != "cuda":
+        kw["transport"] = "nccl"  # CPU: the process group's own reduction (gloo)
     # the fp8 tensor-core path and the tcgen05 attention kernels belong to the fused executor: say so instead of silently
     # training in bf16 / with SDPA
     from ..obs import logger

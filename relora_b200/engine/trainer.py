@@ -13,6 +13,7 @@ reference step for step; what differs is *how* a step executes:
 from __future__ import annotations
 
 import gc
+import math
 import os
 import random
 import time
@@ -468,10 +469,16 @@ def run(args) -> dict:
         has_nan = loss_acc[2] > 0
         uinfo = stepper.update(skip=has_nan, error_if_nonfinite=bool(args.clip_grad_norm > 0 and args.parity_quirks))
         skipped = bool(has_nan)  # one host sync per update (upstream has two: grad_norm.item() and this)
+        if not skipped and not math.isfinite(float(uinfo.grad_norm)):
+            # upstream dies here (clip_grad_norm_(error_if_nonfinite=True), reproduced under --parity_quirks); the kernels have
+            # skipped the update on the device, so the run continues and the event is counted like a NaN loss
+            logger.error(f"Non-finite gradient norm ({float(uinfo.grad_norm)}) at update {st.update_step}, skipping update")
+            skipped = True
         if not skipped:
             scheduler.step()
-        else:
+        elif bool(has_nan):
             logger.error(f"Nan detected in loss_info, loss={float(mean_loss)}, skipping update")
+        if skipped:
             if device.type == "cuda" and hasattr(optimizer, "rollback_skipped_step"):
                 optimizer.rollback_skipped_step()  # the device-side skip left the moments untouched; undo the optimistic step count
             n_skipped += 1
@@ -491,7 +498,8 @@ def run(args) -> dict:
             with phases.phase("save"):
                 ts = asdict(st)
                 ts["update_time"] = update_time
-                ts["dropout_seed"] = _dropout_seed_value(device)
+                if device.type == "cuda":  # engine extension (readers of the reference layout ignore unknown keys)
+                    ts["dropout_seed"] = _dropout_seed_value(device)
                 ckpt_lib.save_checkpoint(model, optimizer=optimizer, scheduler=scheduler, training_state=ts,
                                          run_config=run_config, save_dir=directory, dtype=args.dtype, rank=rank,
                                          barrier=barrier, run_id=sink.id if sink else None)
@@ -574,7 +582,8 @@ def run(args) -> dict:
         logger.info(f"Saving model and optimizer to {directory}, update step {st.update_step}")
         ts = asdict(st)  # incl. n_optimizer_resets (upstream drops it from the final checkpoint; the prune RNG is keyed by it)
         ts["update_time"] = update_time
-        ts["dropout_seed"] = _dropout_seed_value(device)
+        if device.type == "cuda":
+            ts["dropout_seed"] = _dropout_seed_value(device)
         ckpt_lib.save_checkpoint(model, optimizer=optimizer, scheduler=scheduler, training_state=ts,
                                  run_config=run_config, save_dir=directory, dtype=args.dtype, rank=rank,
                                  barrier=barrier, run_id=sink.id if sink else None)

@@ -264,6 +264,16 @@ class FlatAdamW(torch.optim.Optimizer):
         else:
             self._step_t.add_(1.0 - skip.reshape(()).to(self._step_t.dtype).clamp(0, 1))
 
+    def undo_step_if_nonfinite(self, total_norm: torch.Tensor, skip=None) -> None:
+        """Device-side: the kernels skipped this update because the gradient norm was non-finite; take the optimistic count back
+        (unless the update was already skipped -- and not counted -- for a NaN loss)."""
+        bad = (~torch.isfinite(total_norm)).to(self._step_t.dtype).reshape(())
+        if skip is not None and torch.is_tensor(skip):
+            bad = bad * (1.0 - skip.reshape(()).to(self._step_t.dtype).clamp(0, 1))
+        elif skip:
+            return
+        self._step_t.sub_(bad)
+
     def rollback_skipped_step(self) -> None:
         """Host mirror of a skipped update (the trainer calls this after its host-side NaN check)."""
         if self.step_count > 0:
@@ -282,12 +292,16 @@ class FlatAdamW(torch.optim.Optimizer):
             self.advance_step(skip)
             self._native.adamw_flat(p, g, self.exp_avg, self.exp_avg_sq, float(lr), b1, b2, eps, wd,
                                     self.step_count, grad_scale, skip, self._step_t)
+            if torch.is_tensor(grad_scale):
+                self.undo_step_if_nonfinite(grad_scale, skip)
             return None
         if skip is not None and bool(skip):
             return None
+        gs = float(grad_scale) if not torch.is_tensor(grad_scale) else float(grad_scale.item())
+        if not math.isfinite(gs):  # non-finite gradient norm: skip (the native kernels do the same on the device)
+            return None
         self.step_count += 1
         self._step_t.add_(1)
-        gs = float(grad_scale) if not torch.is_tensor(grad_scale) else float(grad_scale.item())
         ref.adamw_step(p, g, self.exp_avg, self.exp_avg_sq, step=self.step_count, lr=lr, beta1=b1, beta2=b2,
                        eps=eps, weight_decay=wd, grad_scale=gs)
         return None

@@ -8,9 +8,10 @@ micro-steps are summed locally and reduced ONCE per update — mathematically id
 Transports:
 
 * ``nccl``  — one ``all_reduce`` (or ``reduce_scatter`` + ``all_gather`` for ZeRO-1) on the flat
-  buffer: the baseline path, also used with gloo on CPU;
-* ``p2p``   — :mod:`relora_b200.parallel.symm_allreduce`: hand-written sm_100a kernels over NVLink
-  peer memory / NVLS multicast, fused with the bf16 cast, the 1/world scale and Σg².
+  buffer: the baseline path implemented here, also used with gloo on CPU;
+* ``p2p``   — :class:`relora_b200.parallel.symm.SymmComm.fused_update`: hand-written sm_100a kernels over NVLink
+  peer memory / NVLS multicast (reduce-scatter + Σg² + AdamW + parameter broadcast in one chain).  The steppers
+  call it directly and bypass :meth:`GradSync.reduce`; ``transport`` is then only a label.
 
 The global gradient norm for clipping is produced here as a device scalar so that the optimizer can
 consume ``clip_coef / world`` without a host synchronisation.
@@ -43,12 +44,10 @@ def broadcast_params(module: torch.nn.Module, src: int = 0) -> None:
 
 
 class GradSync:
-    def __init__(self, store: FlatParamStore, info: DistInfo, *, transport: str = "nccl", zero: bool = False,
-                 symm=None):
+    def __init__(self, store: FlatParamStore, info: DistInfo, *, transport: str = "nccl", zero: bool = False):
         self.store, self.info, self.zero = store, info, zero
         self.world = info.world_size
         self.transport = transport if self.world > 1 else "none"
-        self.symm = symm  # SymmAllReduce instance for transport == "p2p"
         if zero and self.world > 1:
             self.shard = store.shard_bounds(info.rank, self.world)
         else:
@@ -60,9 +59,6 @@ class GradSync:
         if self.world == 1:
             return
         g = self.store.grads
-        if self.transport == "p2p" and self.symm is not None:
-            self.symm.all_reduce_(g) if not self.zero else self.symm.reduce_scatter_(g, self.shard)
-            return
         if self.zero:
             lo, hi = self.shard
             dist.reduce_scatter_tensor(g[lo:hi], g, op=dist.ReduceOp.SUM)
@@ -76,10 +72,7 @@ class GradSync:
             return
         lo, hi = self.shard
         p = self.store.params
-        if self.transport == "p2p" and self.symm is not None and self.symm.owns(p):
-            self.symm.all_gather_(p, self.shard)
-        else:
-            dist.all_gather_into_tensor(p, p[lo:hi].clone())
+        dist.all_gather_into_tensor(p, p[lo:hi].clone())
 
     @torch.no_grad()
     def grad_norm_and_scale(self, max_norm: float) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -98,4 +91,6 @@ class GradSync:
             coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
         else:
             coef = torch.ones_like(total)
+        # a non-finite norm poisons the scale: the optimizer skips the update instead of writing NaNs into the parameters
+        coef = torch.where(torch.isfinite(total), coef, torch.full_like(coef, float("nan")))
         return total, coef / self.world

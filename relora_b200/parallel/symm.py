@@ -45,17 +45,22 @@ class SymmBuffer:
     def __init__(self, tensor: torch.Tensor, handle):
         self.tensor = tensor
         self.handle = handle
-        self.ptrs: List[int] = [int(p) for p in handle.buffer_ptrs]
+        # the tensor may start at a byte offset inside the allocation (torch sub-allocates symmetric memory from a pool in some
+        # configurations): every peer view and the multicast alias are shifted by it, so ptrs[rank] == tensor.data_ptr()
+        off = int(getattr(handle, "offset", 0) or 0)
+        self.base_offset = off
+        self.ptrs: List[int] = [int(p) + off for p in handle.buffer_ptrs]
         mc = 0
         try:
             if handle.has_multicast_support:
-                mc = int(handle.multicast_ptr)
+                mc = int(handle.multicast_ptr) + off
         except Exception:
             mc = 0
         self.mc_base = mc
-        # the tensor may start at an offset inside the allocation
-        off = int(getattr(handle, "offset", 0) or 0)
-        self.base_offset = off
+        rank = int(getattr(handle, "rank", -1))
+        if 0 <= rank < len(self.ptrs) and self.ptrs[rank] != tensor.data_ptr():
+            raise RuntimeError(f"symmetric buffer: local peer view {self.ptrs[rank]:#x} does not alias the tensor ({tensor.data_ptr():#x}, "
+                               f"offset {off})")
 
     def mc_ptr(self, use_multicast: bool) -> int:
         return self.mc_base if (use_multicast and self.mc_base) else 0
@@ -123,7 +128,7 @@ class SymmComm:
         self.C.comm_allreduce_bf16(self.flags.ptrs, self.rank, self.world, self.local_go, buf.ptrs, buf.mc_ptr(self.use_multicast),
                                    off_elems, n, self._next_epoch(), self.max_blocks)
 
-    def fused_update(self, *, grads_f32: torch.Tensor, grad_buf: SymmBuffer, gred: torch.Tensor, param_buf: SymmBuffer,
+    def fused_update(self, *, grads_f32: Optional[torch.Tensor], grad_buf: SymmBuffer, gred: torch.Tensor, param_buf: SymmBuffer,
                      exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, n: int, lr: float, betas: Tuple[float, float], eps: float,
                      weight_decay: float, step: int, max_norm: float, skip: Optional[torch.Tensor],
                      step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -68,6 +68,43 @@ def check_training(rank, world, transport):
     return {"losses": losses, "checksum": chk, "transport": eng.stepper.sync.transport, "executor": type(eng.stepper).__name__}
 
 
+def _replicas_equal(p):
+    chk = torch.tensor([float(p.float().sum()), float(p.float().abs().sum()), float(p[::997].double().sum())], dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi)), chk.tolist()
+
+
+def check_long_training(rank, world, transport, steps=60, use_peft=True):
+    """`steps` updates with DP = world (through one ReLoRA merge + optimizer reset when use_peft): every loss, gradient norm and
+    parameter must stay finite and the replicas bit-identical.  (Round-1 driver run: NaN after ~10 updates at 4 and 8 GPUs.)"""
+    from relora_b200.engine.api import TrainingEngine
+    from relora_b200.parallel.dist import init_distributed
+
+    info = init_distributed("cuda", "nccl")
+    kw = dict(use_peft=True, lora_r=128, relora=25, cycle_length=25, init_lora_a="kaiming") if use_peft else dict(use_peft=False)
+    eng = TrainingEngine.build(info, model_config=os.path.join(ROOT, "configs", "llama_35m.json"), batch_size=4,
+                               gradient_accumulation=2, total_batch_size=8 * world, max_length=256, scheduler="cosine_restarts" if use_peft else "cosine",
+                               warmup_steps=5, restart_warmup_steps=2, lr=1e-3, num_training_steps=100, dtype="bfloat16", device="cuda",
+                               comm=transport, seed=0, **kw)
+    g = torch.Generator().manual_seed(1234 + rank)  # bench.py's per-rank token streams
+    losses, norms = [], []
+    for s in range(steps):
+        ids = torch.randint(0, 32099, (2, 4, 256), generator=g).cuda()
+        losses.append(float(eng.train_step_device(ids)))
+        norms.append(float(eng.last_grad_norm))
+        if (s + 1) % 10 == 0:
+            p = eng.stepper.store.params
+            assert bool(torch.isfinite(p.float()).all()), f"non-finite parameters after update {s}"
+            same, chk = _replicas_equal(p)
+            assert same, ("replicas diverged", s, chk)
+    assert all(l == l and abs(l) < 1e4 for l in losses), losses
+    assert all(n == n and n < 1e6 for n in norms), norms
+    return {"losses": losses[::10] + [losses[-1]], "norms": norms[::10], "transport": eng.stepper.sync.transport,
+            "executor": type(eng.stepper).__name__, "restarts": eng.n_lora_restarts, "steps": steps}
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -79,6 +116,10 @@ def main():
 
         comm = SymmComm()
         res = check_allreduce(comm, rank, world)
+    elif mode.startswith("long_"):       # long_p2p | long_nccl
+        res = check_long_training(rank, world, mode.split("_", 1)[1])
+    elif mode.startswith("module_"):     # module_p2p | module_nccl: full-rank training on the module path
+        res = check_long_training(rank, world, mode.split("_", 1)[1], steps=30, use_peft=False)
     elif mode.startswith("train_"):
         res = check_training(rank, world, mode.split("_", 1)[1])
     if rank == 0:

@@ -346,6 +346,17 @@ def test_embedding(C):
     want = torch.zeros(V, H, device="cuda").index_add_(0, ids, dout.float())
     want[V - 1] = 0
     assert _relerr(dt, want) < 1e-5
+    # deterministic variant (stable sort, one writer per row): same values, bit-identical across repetitions and when
+    # accumulating on top of an existing gradient
+    sid, perm = torch.sort(ids, stable=True)
+    runs = []
+    for _ in range(3):
+        d2 = torch.full((V, H), 0.25, device="cuda", dtype=torch.float32)
+        C.embedding_bwd_sorted(sid, perm, dout, d2, V - 1)
+        runs.append(d2)
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    assert _relerr(runs[0] - 0.25, want) < 1e-5
+    assert float(runs[0][V - 1].sub(0.25).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("V", [32100, 1000, 50257])

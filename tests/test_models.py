@@ -130,3 +130,32 @@ def test_rope_scaling_variants():
     inv_before = dyn.inv_freq.clone()
     dyn(x, 64)  # beyond the trained context: base grows
     assert not torch.equal(inv_before, dyn.inv_freq) and dyn.cos_cached.shape[2] == 64
+
+
+def test_sequence_starting_with_the_padding_row_overflows_the_reference_gradient(reference_modules):
+    """Root cause of round 1's non-finite 4-/8-GPU benchmark runs (both arms).  The configs' ``pad_token_id = -1`` makes row V-1
+    the embedding's zero padding row; a sequence that *starts* with it keeps an exactly-zero residual row through every layer
+    (v = 0, no biases), and RMSNorm's backward at x = 0 multiplies the gradient by 1/sqrt(eps) = 1000 per norm: it overflows
+    fp32 within ~12 layers of the *unmodified reference model*.  Synthetic token generators therefore never emit that id
+    (real tokenised text does not contain it either)."""
+    from transformers import AutoConfig
+
+    from relora_b200.data.synthetic import SyntheticTokens
+
+    hf_cfg = AutoConfig.from_pretrained("/root/reference/configs/llama_35m.json")
+    hf_cfg.num_hidden_layers = 12
+    V = hf_cfg.vocab_size
+    torch.manual_seed(0)
+    model = reference_modules.llama.LlamaForCausalLM(hf_cfg)
+    norms = {}
+    for first in (5, V - 1):
+        ids = torch.randint(0, V - 1, (2, 48))
+        ids[0, 0] = first
+        emb = model.model.embed_tokens(ids).detach().requires_grad_()
+        model(inputs_embeds=emb, labels=ids).loss.backward()
+        norms[first] = float(emb.grad[0, 0].norm())
+    assert norms[5] < 1e3                       # ordinary token: ordinary gradient
+    assert not (norms[V - 1] < 1e30)            # padding row first: overflow (inf / nan)
+    # ... which is why the synthetic sources draw from [0, V - 1)
+    ds = SyntheticTokens(64, 128, V, seed=3)
+    assert max(int(ds[i]["input_ids"].max()) for i in range(64)) < V - 1

@@ -43,3 +43,21 @@ def test_fused_update_p2p_matches_nccl_training():
         assert abs(x - y) < 5e-2, (a, b)
     # same data, same seeds: parameters agree up to bf16 reduction-order noise
     assert abs(a["checksum"][1] - b["checksum"][1]) / abs(a["checksum"][1]) < 1e-3, (a, b)
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_sixty_updates_stay_finite_and_replicated(transport):
+    """60 updates at world = all visible GPUs through two ReLoRA resets: finite losses / norms / parameters, identical replicas."""
+    res = _run(f"long_{transport}", nproc=_nproc(), port=29651 if transport == "p2p" else 29653, timeout=900)
+    assert res["transport"] == transport and res["executor"] == "FusedLlamaStepper"
+    assert res["restarts"] >= 2 and res["steps"] == 60
+    assert all(l == l for l in res["losses"])
+
+
+def test_module_path_uses_the_peer_memory_update():
+    """Full-rank Llama (module path, no fused executor): the hand-written NVLink update is the transport, and it tracks NCCL."""
+    a = _run("module_p2p", nproc=_nproc(), port=29655, timeout=900)
+    b = _run("module_nccl", nproc=_nproc(), port=29657, timeout=900)
+    assert a["transport"] == "p2p" and b["transport"] == "nccl"
+    assert a["executor"] == b["executor"] == "ModuleStepper"
+    assert abs(a["losses"][-1] - b["losses"][-1]) < 0.15, (a, b)

@@ -41,7 +41,7 @@ def test_zero1_matches_replicated_adam(tmp_path):
     sa = torch.load(os.path.join(a, "model_4", "pytorch_model.bin"), weights_only=True)
     sb = torch.load(os.path.join(b, "model_4", "pytorch_model.bin"), weights_only=True)
     for k in sa:
-        assert torch.allclose(sa[k], sb[k], atol=1e-6), k
+        assert torch.allclose(sa[k], sb[k], atol=5e-6), k  # fp32 reduction-order noise (reduce_scatter vs all_reduce)
     oa = torch.load(os.path.join(a, "model_4", "optimizer.pt"), weights_only=False)["optimizer"]
     ob = torch.load(os.path.join(b, "model_4", "optimizer.pt"), weights_only=False)["optimizer"]
     assert set(oa["state"]) == set(ob["state"])  # consolidated: every parameter has state on rank 0
