@@ -75,20 +75,40 @@ __device__ __forceinline__ void mc_st(void* mc, const uint4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// All `WORLD` peer loads of one 16-byte vector are issued before the first add (the loop is fully unrolled), so a thread keeps
+// WORLD x U requests in flight across the ~2 us NVLink round trip instead of one.
+template <int WORLD>
+__device__ __forceinline__ void reduce_vec_p2p(const PeerPtrs& bufs, int rank, long long vec_index, float (&acc)[8]) {
+  uint4 raw[WORLD];
+#pragma unroll
+  for (int k = 0; k < WORLD; ++k) {
+    const int p = (rank + k) % WORLD;  // start with the local copy, spread the first remote requests over peers
+    raw[k] = ld_peer(reinterpret_cast<const uint4*>(bufs.ptr[p]) + vec_index);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < WORLD; ++k) {
+    float f[8];
+    unpack8(raw[k], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+}
 __device__ __forceinline__ void reduce_vec(const PeerPtrs& bufs, const void* mc, int world, int rank, long long vec_index, float (&acc)[8]) {
   if (mc != nullptr) {
     unpack8(mc_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(mc) + vec_index), acc);
     return;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 1
-  for (int k = 0; k < world; ++k) {
-    const int p = (rank + k) % world;  // start with the local copy, spread the first remote requests over peers
-    float f[8];
-    unpack8(ld_peer(reinterpret_cast<const uint4*>(bufs.ptr[p]) + vec_index), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  switch (world) {
+    case 2: reduce_vec_p2p<2>(bufs, rank, vec_index, acc); break;
+    case 3: reduce_vec_p2p<3>(bufs, rank, vec_index, acc); break;
+    case 4: reduce_vec_p2p<4>(bufs, rank, vec_index, acc); break;
+    case 5: reduce_vec_p2p<5>(bufs, rank, vec_index, acc); break;
+    case 6: reduce_vec_p2p<6>(bufs, rank, vec_index, acc); break;
+    case 7: reduce_vec_p2p<7>(bufs, rank, vec_index, acc); break;
+    case 8: reduce_vec_p2p<8>(bufs, rank, vec_index, acc); break;
+    default: reduce_vec_p2p<1>(bufs, rank, vec_index, acc); break;
   }
 }
 __device__ __forceinline__ void broadcast_vec(const PeerPtrs& bufs, void* mc, int world, long long vec_index, const uint4& v) {
@@ -172,37 +192,59 @@ __global__ void __launch_bounds__(512) reduce_scatter_kernel(const CommCtx c, co
   __shared__ float scratch[32];
   const long long lo = chunk_vec * c.rank;
   float sq = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < chunk_vec; i += (long long)gridDim.x * blockDim.x) {
-    float acc[8];
-    reduce_vec(bufs, mc, c.world, c.rank, lo + i, acc);
+  constexpr int U = 2;  // independent vectors per thread per trip (x world peer loads each)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < chunk_vec; i0 += stride * U) {
+    float acc[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sq += acc[j] * acc[j];
-    reinterpret_cast<float4*>(gred)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    reinterpret_cast<float4*>(gred)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < chunk_vec) reduce_vec(bufs, mc, c.world, c.rank, lo + i, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < chunk_vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq += acc[u][j] * acc[u][j];
+        reinterpret_cast<float4*>(gred)[2 * i] = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        reinterpret_cast<float4*>(gred)[2 * i + 1] = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+      }
+    }
   }
   sq = block_sum(sq, scratch);
   if (threadIdx.x == 0) atomicAdd(sq_accum, sq);
 }
 
-// one block: publish this rank's sum(g^2) to every peer, barrier, combine -> clip coefficient
+// one block: publish this rank's sum(g^2) -- and its mean loss / NaN flag, the reference's `loss_info` all-reduce (torchrun_main.py:810)
+// -- to every peer, barrier, combine -> clip coefficient, mean loss over ranks, "skip if any rank saw a NaN loss"
 __global__ void norm_exchange_kernel(const CommCtx c, const float* __restrict__ sq_accum, float max_norm, float inv_world, uint32_t epoch,
-                                     float* __restrict__ grad_scale, float* __restrict__ norm_out) {
+                                     float* __restrict__ grad_scale, float* __restrict__ norm_out, const float* __restrict__ loss_in,
+                                     const float* __restrict__ skip_in, float* __restrict__ loss_out, float* __restrict__ skip_out) {
   const int t = threadIdx.x;
   if (t < c.world) {
     float* slot = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(c.flags.ptr[t]) + 4 * kMaxPeers) + c.rank;
     *reinterpret_cast<volatile float*>(slot) = *sq_accum;
+    *reinterpret_cast<volatile float*>(slot + kMaxPeers) = loss_in != nullptr ? *loss_in : 0.f;
+    *reinterpret_cast<volatile float*>(slot + 2 * kMaxPeers) = skip_in != nullptr ? *skip_in : 0.f;
   }
   barrier_threads(c, 2, epoch);
   if (t == 0) {
     const volatile float* mine = reinterpret_cast<const volatile float*>(reinterpret_cast<const uint32_t*>(c.flags.ptr[c.rank]) + 4 * kMaxPeers);
-    float tot = 0.f;
-    for (int p = 0; p < c.world; ++p) tot += mine[p];
+    float tot = 0.f, loss = 0.f, skip = 0.f;
+    for (int p = 0; p < c.world; ++p) {
+      tot += mine[p];
+      loss += mine[kMaxPeers + p];
+      skip += (mine[2 * kMaxPeers + p] != 0.f) ? 1.f : 0.f;  // fixed order: bit-identical on every rank
+    }
     const float norm = sqrtf(tot) * inv_world;  // norm of the rank-averaged gradient
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
     // a non-finite gradient norm poisons the scale on purpose: the Adam stage skips the update (see adam_allgather_kernel)
     *grad_scale = (norm < INFINITY) ? coef * inv_world : __int_as_float(0x7fc00000);
     *norm_out = norm;
+    if (loss_out != nullptr) *loss_out = loss * inv_world;
+    *skip_out = skip;
   }
 }
 
@@ -256,13 +298,15 @@ void fused_update(const CommCtx& c, const FusedUpdateArgs& a, uint32_t epoch0, c
   reduce_scatter_kernel<<<blocks, 512, 0, s>>>(c, a.grad_bufs, a.grad_mc, chunk_vec, a.gred, a.sq_accum);
   RB_CHECK_LAUNCH("reduce_scatter");
   float* grad_scale = a.sq_accum + 1;
-  norm_exchange_kernel<<<1, 32, 0, s>>>(c, a.sq_accum, a.max_norm, a.inv_world, epoch0, grad_scale, a.norm_out);
+  float* skip_all = a.sq_accum + 2;  // "some rank saw a NaN loss" (or the caller's already-global flag)
+  norm_exchange_kernel<<<1, 32, 0, s>>>(c, a.sq_accum, a.max_norm, a.inv_world, epoch0, grad_scale, a.norm_out, a.loss_in, a.skip, a.loss_out,
+                                        skip_all);
   RB_CHECK_LAUNCH("norm_exchange");
   const float bc1_inv = 1.f / (1.f - powf(a.beta1, (float)a.step));
   const float bc2_rsqrt = 1.f / sqrtf(1.f - powf(a.beta2, (float)a.step));
   adam_allgather_kernel<<<blocks, 512, 0, s>>>(c, a.param_bufs, a.param_mc, chunk_vec, a.gred, reinterpret_cast<bf16*>(a.exp_avg),
                                                reinterpret_cast<bf16*>(a.exp_avg_sq), a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, bc1_inv,
-                                               bc2_rsqrt, grad_scale, a.skip, a.step_dev);
+                                               bc2_rsqrt, grad_scale, skip_all, a.step_dev);
   RB_CHECK_LAUNCH("adam_allgather");
   xgpu_barrier(c, 1, epoch0, s);  // every replica holds the new parameters before the next forward starts
 }

@@ -51,9 +51,11 @@ struct FusedUpdateArgs {
   const float* step_dev;    // device-resident step count (nullable): replaces `step` in the bias corrections
   float max_norm;           // <= 0: no clipping
   float inv_world;          // gradients are averaged over ranks
-  const float* skip;        // device flag (nullable): != 0 -> no update
+  const float* skip;        // device flag (nullable): != 0 on ANY rank -> no update on every rank (combined in the norm exchange)
+  const float* loss_in;     // this rank's mean loss (nullable); the mean over ranks lands in loss_out  [replaces the NCCL all-reduce
+  float* loss_out;          //   of the reference's loss_info, torchrun_main.py:810]
   float* norm_out;          // device float: total gradient norm (averaged gradient)
-  float* sq_accum;          // device float scratch (zeroed by the call)
+  float* sq_accum;          // device float[3] scratch: sum(g^2) (zeroed by the call), grad scale, combined skip flag
   int max_blocks;
 };
 void fused_update(const CommCtx& c, const FusedUpdateArgs& a, uint32_t epoch0, cudaStream_t s);

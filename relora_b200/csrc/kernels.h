@@ -52,6 +52,19 @@ void swiglu_fwd(const void* gu, long long ldgu, void* h, long long ldh, int M, i
 void swiglu_bwd(const void* dh, long long lddh, const void* gu, long long ldgu, void* dgu, long long lddgu, int M, int F,
                 cudaStream_t s);
 
+// ---- GPT-NeoX / Pythia block (neox.cu) -------------------------------------------------------
+// nn.LayerNorm (affine weight + optional bias), bf16 in/out, fp32 row statistics saved for the backward; false = shape not handled
+bool layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int M, int H, float eps, cudaStream_t s);
+// dw / db (fp32, may be nullptr for db) are accumulated (+=)
+bool layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, float* dw, float* db, int M,
+                   int H, cudaStream_t s);
+void gelu_fwd(const void* z, void* a, long long n, bool tanh_approx, cudaStream_t s);
+void gelu_bwd(const void* da, const void* z, void* dz, long long n, bool tanh_approx, cudaStream_t s);
+// partial rotary embedding in place on the fused query_key_value output [rows, nh, 3*hd] (q | k | v per head); fp32 tables [n_pos, rot]
+// holding the cos / sin of the first rot/2 frequencies twice (HF layout: emb = cat(freqs, freqs)); inverse = backward direction
+void neox_rope(void* qkv, long long ld, long long rows, int T, int nh, int hd, int rot, const float* cos, const float* sin, int pos0,
+               bool inverse, cudaStream_t s);
+
 // ---- embedding -----------------------------------------------------------------------------
 void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int H, cudaStream_t s);
 // dtable_f32[ids[m], :] += dout[m, :]   (skips padding_idx)

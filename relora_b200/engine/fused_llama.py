@@ -267,10 +267,10 @@ class FusedLlamaStepper:
         native_ok = self.hd % 8 == 0 and self.hd <= 64
         if attention == "native" and not native_ok:
             raise RuntimeError(f"--attention native supports head_dim <= 64 (multiple of 8), got {self.hd}")
-        # auto: torch SDPA (cuDNN's sm100 flash kernels) while it is the faster of the two -- measured on B200 (bench/attn_bench.py):
-        # forward 74 vs 48 us, backward 202 vs 135 us at B 24 x T 512 x 16 heads x 48; the tcgen05 kernels are selected with
-        # --attention native (tests/test_kernels_gpu.py::test_attention_fwd_bwd, test_native_attention_matches_sdpa_in_the_executor)
-        self.native_attn = attention == "native"
+        # auto: this repo's tcgen05 kernels (csrc/attention.cu) wherever they apply -- the hot path then contains no library
+        # attention call; `--attention sdpa` selects torch SDPA (cuDNN's sm100 kernels; measured per layer at B 24 x T 512 x 16 x 48
+        # in bench/attn_bench.py, see profiles/) and is what larger head dims fall back to
+        self.native_attn = attention == "native" or (attention == "auto" and native_ok)
         self.side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
         self.fused_dx = os.environ.get("RELORA_B200_FUSED_DX", "1") != "0"
         # stacked output width from which dx uses two kernels (frozen-path GEMM on 256-wide / CTA-pair tiles + a mask-and-add pass).

@@ -187,10 +187,24 @@ class LlamaAttention(nn.Module):
             # chunked prefill onto a cache: lower-right aligned causal mask
             mask = torch.ones(T, kv_len, dtype=torch.bool, device=q.device).tril(diagonal=kv_len - T)
             out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+        elif causal and past_key_value is None and _use_native_attention(q, self.head_dim):
+            # this repo's tcgen05 flash-attention kernels (csrc/attention.cu) instead of the library SDPA call
+            from ..ops import fused
+
+            out = fused.causal_attention(q, k, v)
         else:
             out = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=causal)
         out = out.transpose(1, 2).reshape(B, T, self.hidden_size)
         return self.o_proj(out), present
+
+
+def _use_native_attention(q: torch.Tensor, head_dim: int) -> bool:
+    """CUDA + bf16 + head_dim <= 64 (multiple of 8): the tcgen05 kernels; RELORA_B200_ATTENTION=sdpa forces the library call."""
+    if not q.is_cuda or os.environ.get("RELORA_B200_ATTENTION", "auto") == "sdpa":
+        return False
+    from ..ops import dispatch, fused
+
+    return dispatch.use_fused(q) and fused.native_attention_supported(q, head_dim)
 
 
 class LlamaDecoderLayer(nn.Module):

@@ -133,6 +133,9 @@ class GPTNeoXAttention(nn.Module):
     def forward(self, hidden_states, attention_mask, position_ids, layer_past=None, use_cache=False):
         B, T, _ = hidden_states.shape
         qkv = self.query_key_value(hidden_states).view(B, T, self.num_attention_heads, 3 * self.head_size)
+        if (layer_past is None and not use_cache and getattr(position_ids, "_rb_default", False) and _native(qkv)
+                and self.rotary_ndims % 2 == 0 and not self.training_dropout_active()):
+            return self._forward_native(qkv, B, T)
         q = qkv[..., : self.head_size].permute(0, 2, 1, 3)
         k = qkv[..., self.head_size : 2 * self.head_size].permute(0, 2, 1, 3)
         v = qkv[..., 2 * self.head_size :].permute(0, 2, 1, 3)
@@ -164,6 +167,46 @@ class GPTNeoXAttention(nn.Module):
         return self.dense(out), present
 
 
+    def training_dropout_active(self) -> bool:
+        return self.training and self.dropout_prob_attn > 0.0
+
+    def _forward_native(self, qkv, B, T):
+        """CUDA / bf16 training path: partial rotary in place on the fused projection output (csrc/neox.cu), then causal attention
+        on the tcgen05 kernels when the head size allows (<= 64), torch SDPA otherwise.  Positions are 0..T-1 (no cache)."""
+        from ..ops import fused
+
+        nh, hd, rd = self.num_attention_heads, self.head_size, self.rotary_ndims
+        cos, sin = self.rotary_emb(qkv, seq_len=T)
+        qkv = fused.neox_rope(qkv, cos[0, 0].float().contiguous(), sin[0, 0].float().contiguous(), nh, hd, rd)
+        q = qkv[..., :hd].permute(0, 2, 1, 3)
+        k = qkv[..., hd : 2 * hd].permute(0, 2, 1, 3)
+        v = qkv[..., 2 * hd :].permute(0, 2, 1, 3)
+        if fused.native_attention_supported(q, hd) and os.environ.get("RELORA_B200_ATTENTION", "auto") != "sdpa":
+            out = fused.causal_attention(q, k, v)
+        else:
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=T > 1)
+        out = out.permute(0, 2, 1, 3).reshape(B, T, self.hidden_size)
+        return self.dense(out), None
+
+
+def _native(x: torch.Tensor) -> bool:
+    """CUDA + bf16 (and the extension present): the leaf ops of this file dispatch to csrc/neox.cu."""
+    if not x.is_cuda:
+        return False
+    from ..ops import dispatch
+
+    return dispatch.use_fused(x)
+
+
+def _layer_norm(mod: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    if _native(x) and mod.elementwise_affine:
+        from ..ops import fused
+
+        if fused.layernorm_supported(x):
+            return fused.layernorm(x, mod.weight, mod.bias, mod.eps)
+    return mod(x)
+
+
 class GPTNeoXMLP(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -182,7 +225,14 @@ class GPTNeoXMLP(nn.Module):
             raise NotImplementedError(f"hidden_act={act}")
 
     def forward(self, x):
-        return self.dense_4h_to_h(self.act(self.dense_h_to_4h(x)))
+        z = self.dense_h_to_4h(x)
+        if isinstance(self.act, nn.GELU) and _native(z) and z.numel() % 8 == 0:
+            from ..ops import fused
+
+            a = fused.gelu(z, tanh_approx=self.act.approximate == "tanh")
+        else:
+            a = self.act(z)
+        return self.dense_4h_to_h(a)
 
 
 class GPTNeoXLayer(nn.Module):
@@ -198,15 +248,15 @@ class GPTNeoXLayer(nn.Module):
         self.mlp = GPTNeoXMLP(config)
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, layer_past=None, use_cache=False):
-        attn, present = self.attention(self.input_layernorm(hidden_states), attention_mask, position_ids, layer_past, use_cache)
+        attn, present = self.attention(_layer_norm(self.input_layernorm, hidden_states), attention_mask, position_ids, layer_past, use_cache)
         attn = self.post_attention_dropout(attn)
         if self.use_parallel_residual:
             # x = x + attn(ln1(x)) + mlp(ln2(x))
-            mlp = self.post_mlp_dropout(self.mlp(self.post_attention_layernorm(hidden_states)))
+            mlp = self.post_mlp_dropout(self.mlp(_layer_norm(self.post_attention_layernorm, hidden_states)))
             hidden_states = mlp + attn + hidden_states
         else:
             attn = attn + hidden_states
-            mlp = self.post_mlp_dropout(self.mlp(self.post_attention_layernorm(attn)))
+            mlp = self.post_mlp_dropout(self.mlp(_layer_norm(self.post_attention_layernorm, attn)))
             hidden_states = mlp + attn
         return hidden_states, present
 
@@ -288,10 +338,13 @@ class GPTNeoXModel(nn.Module, _NeoXMixin):
             inputs_embeds = self.embed_in(input_ids)
         B, T, _ = inputs_embeds.shape
         past_len = past_key_values[0][0].size(-2) if past_key_values is not None else 0
+        default_positions = position_ids is None and past_len == 0
         if position_ids is None:
             position_ids = torch.arange(past_len, T + past_len, dtype=torch.long, device=inputs_embeds.device).unsqueeze(0).expand(B, T)
         else:
             position_ids = position_ids.view(-1, T).long()
+        if default_positions:
+            position_ids._rb_default = True  # positions 0..T-1: lets the attention take the in-place rotary kernel
         if attention_mask is not None:
             am = attention_mask.view(B, -1)[:, None, None, :].to(dtype=inputs_embeds.dtype)
             attention_mask = (1.0 - am) * torch.finfo(inputs_embeds.dtype).min
@@ -310,7 +363,7 @@ class GPTNeoXModel(nn.Module, _NeoXMixin):
                 h, present = layer(h, attention_mask, position_ids, past, use_cache)
             if cache is not None:
                 cache.append(present)
-        h = self.final_layer_norm(h)
+        h = _layer_norm(self.final_layer_norm, h)
         if all_h is not None:
             all_h.append(h)
         return h, cache, all_h

@@ -154,6 +154,92 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     return _RMSNormFn.apply(x, weight, eps)
 
 
+# ----------------------------------------------------------------------------- GPT-NeoX / Pythia leaf ops (csrc/neox.cu)
+class _LayerNormFn(torch.autograd.Function):
+    """``nn.LayerNorm`` with affine weight / bias (reference modeling_pythia.py:413-414) on the warp-per-row kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        y = torch.empty_like(x2)
+        mean = torch.empty(x2.shape[0], dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        _C().layernorm_fwd(x2, weight.contiguous(), None if bias is None else bias.contiguous(), y, mean, rstd, float(eps))
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.shape = shp
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape).contiguous()
+        dx = torch.empty_like(x2)
+        dw = torch.zeros(x2.shape[1], dtype=torch.float32, device=x2.device)
+        db = torch.zeros_like(dw) if ctx.has_bias else None
+        _C().layernorm_bwd(dy2, x2, weight.contiguous(), mean, rstd, dx, dw, db)
+        return dx.view(ctx.shape), dw.to(weight.dtype), (db.to(weight.dtype) if db is not None else None), None
+
+
+def layernorm_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == _BF16 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 2048
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    return _LayerNormFn.apply(x, weight, bias, eps)
+
+
+class _GeluFn(torch.autograd.Function):
+    """Exact (erf) or tanh GELU (reference modeling_pythia.py:395-406); the backward recomputes the derivative from the input."""
+
+    @staticmethod
+    def forward(ctx, z, tanh_approx):
+        zc = z.contiguous()
+        a = torch.empty_like(zc)
+        _C().gelu_fwd(zc, a, bool(tanh_approx))
+        ctx.save_for_backward(zc)
+        ctx.tanh_approx = bool(tanh_approx)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        (z,) = ctx.saved_tensors
+        dz = torch.empty_like(z)
+        _C().gelu_bwd(da.contiguous(), z, dz, ctx.tanh_approx)
+        return dz, None
+
+
+def gelu(z: torch.Tensor, tanh_approx: bool = False) -> torch.Tensor:
+    return _GeluFn.apply(z, tanh_approx)
+
+
+class _NeoXRopeFn(torch.autograd.Function):
+    """Partial rotary embedding on the fused ``query_key_value`` output ``[B, T, nh, 3*hd]`` (reference modeling_pythia.py:172-197):
+    the first ``rot`` dims of q and k of every head are rotated with fp32 tables; backward applies the inverse rotation."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, nh, hd, rot):
+        B, T = qkv.shape[0], qkv.shape[1]
+        out = qkv.reshape(B * T, nh * 3 * hd).clone()
+        _C().neox_rope(out, T, nh, hd, rot, cos, sin, 0, False)
+        ctx.save_for_backward(cos, sin)
+        ctx.meta = (B, T, nh, hd, rot, qkv.shape)
+        return out.view(qkv.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        cos, sin = ctx.saved_tensors
+        B, T, nh, hd, rot, shp = ctx.meta
+        gg = g.reshape(B * T, nh * 3 * hd).clone()
+        _C().neox_rope(gg, T, nh, hd, rot, cos, sin, 0, True)
+        return gg.view(shp), None, None, None, None, None
+
+
+def neox_rope(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, nh: int, hd: int, rot: int) -> torch.Tensor:
+    return _NeoXRopeFn.apply(qkv, cos, sin, nh, hd, rot)
+
+
 # ----------------------------------------------------------------------------- LoRA linear (module path)
 class _LoRALinearFn(torch.autograd.Function):
     """y = x Wᵀ + s·drop(x) Aᵀ Bᵀ with the low-rank up-projection folded into the frozen GEMM's K loop.
@@ -249,6 +335,57 @@ def relora_linear_module(module, x: torch.Tensor) -> torch.Tensor:
         return out + module.lora_B(module.lora_A(xd)) * module._post_lora_scale()
     return _LoRALinearFn.apply(x, module.weight, module.lora_A.weight, module.lora_B.weight, float(module.scaling),
                                float(module.lora_dropout.p), int(module.module_index) + 1, module.training, module.bias)
+
+
+# ----------------------------------------------------------------------------- causal attention (module path)
+def native_attention_supported(q: torch.Tensor, head_dim: int) -> bool:
+    """The tcgen05 attention kernels (csrc/attention.cu): CUDA bf16, head_dim a multiple of 8 and <= 64."""
+    return q.is_cuda and q.dtype == _BF16 and head_dim % 8 == 0 and head_dim <= 64
+
+
+class _CausalAttentionFn(torch.autograd.Function):
+    """Causal self-attention on the tcgen05 kernels for ``q, k, v [B, nh, T, hd]`` (RoPE already applied).
+
+    The kernels read a packed ``[B*T, 3*nh*hd]`` projection buffer in place (that is what the fused executor hands them);
+    the module path packs its three projection outputs once.  Replaces ``F.scaled_dot_product_attention(is_causal=True)``
+    (reference modeling_llama.py:222-224)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale):
+        C = _C()
+        B, nh, T, hd = q.shape
+        M, h = B * T, nh * hd
+        qkv = torch.empty(M, 3 * h, dtype=_BF16, device=q.device)
+        q5 = qkv.view(B, T, 3, nh, hd)
+        q5[:, :, 0].copy_(q.transpose(1, 2))
+        q5[:, :, 1].copy_(k.transpose(1, 2))
+        q5[:, :, 2].copy_(v.transpose(1, 2))
+        out = torch.empty(M, h, dtype=_BF16, device=q.device)
+        lse = torch.empty(B, nh, T, dtype=torch.float32, device=q.device)
+        C.attention_fwd(qkv, out, lse, B, T, nh, hd, float(scale))
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (B, nh, T, hd, float(scale))
+        return out.view(B, T, nh, hd).transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        C = _C()
+        qkv, out, lse = ctx.saved_tensors
+        B, nh, T, hd, scale = ctx.meta
+        M, h = B * T, nh * hd
+        do = dout.transpose(1, 2).reshape(M, h)
+        if not do.is_contiguous():
+            do = do.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device)
+        C.attention_bwd(qkv, out, do, lse, delta, dqkv, B, T, nh, hd, scale)
+        d5 = dqkv.view(B, T, 3, nh, hd)
+        return d5[:, :, 0].transpose(1, 2), d5[:, :, 1].transpose(1, 2), d5[:, :, 2].transpose(1, 2), None
+
+
+def causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None) -> torch.Tensor:
+    hd = q.shape[-1]
+    return _CausalAttentionFn.apply(q, k, v, (1.0 / math.sqrt(hd)) if scale is None else scale)
 
 
 # ----------------------------------------------------------------------------- LM head + cross entropy

@@ -87,7 +87,8 @@ class SymmComm:
         flags.tensor.zero_()
         self.flags = flags
         self.local_go = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self.scratch = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.scratch = torch.zeros(4, dtype=torch.float32, device=self.device)  # sum(g^2), grad scale, combined skip flag
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.norm_out = torch.zeros(1, dtype=torch.float32, device=self.device)
         torch.cuda.synchronize()
         dist.barrier(self.group)
@@ -131,11 +132,19 @@ class SymmComm:
     def fused_update(self, *, grads_f32: Optional[torch.Tensor], grad_buf: SymmBuffer, gred: torch.Tensor, param_buf: SymmBuffer,
                      exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, n: int, lr: float, betas: Tuple[float, float], eps: float,
                      weight_decay: float, step: int, max_norm: float, skip: Optional[torch.Tensor],
-                     step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     step_dev: Optional[torch.Tensor] = None, local_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Returns the gradient norm (device).  ``skip`` / ``local_loss`` are this rank's values: the kernel chain combines them over
+        ranks (``self.skip_all``: number of ranks that asked to skip, ``self.loss_out``: mean loss) without an NCCL call."""
         sk = None if skip is None else skip.reshape(1).float()
+        ll = None if local_loss is None else local_loss.reshape(1).float()
         self.C.comm_fused_update(self.flags.ptrs, self.rank, self.world, self.local_go, grads_f32, grad_buf.ptrs,
                                  grad_buf.mc_ptr(self.use_multicast), gred, param_buf.ptrs, param_buf.mc_ptr(self.use_multicast),
                                  exp_avg, exp_avg_sq, n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                  int(step), float(max_norm), sk, self.norm_out, self.scratch, self._next_epoch(), self.max_blocks,
-                                 None if step_dev is None else step_dev.reshape(1).float())
+                                 None if step_dev is None else step_dev.reshape(1).float(), ll, self.loss_out if ll is not None else None)
         return self.norm_out
+
+    @property
+    def skip_all(self) -> torch.Tensor:
+        """Device scalar written by the last fused_update: how many ranks requested a skip (0 = the update was applied)."""
+        return self.scratch[2]

@@ -411,13 +411,19 @@ def test_adamw_flat(C, gdt, sdt):
     v = (0.01 * torch.rand(n, device="cuda")).to(sdt)
     p2, m2, v2 = p.clone(), m.clone(), v.clone()
     gs = torch.tensor([0.5], device="cuda")
-    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 7, gs, 1.0, None)
+    # the bias corrections come from the device-resident step count (7) when one is passed; the host value (99) is then ignored
+    step_dev = torch.tensor([7.0], device="cuda")
+    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 99, gs, 1.0, None, step_dev)
     ref.adamw_step(p2, g, m2, v2, step=7, lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.01, grad_scale=0.5)
     assert _relerr(p, p2) < 1e-3 and _relerr(m, m2) < 4e-3 and _relerr(v, v2) < 4e-3
     # device-side skip leaves everything untouched
-    before = p.clone()
-    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 8, None, 1.0, torch.ones(1, device="cuda"))
+    before, mb, vb = p.clone(), m.clone(), v.clone()
+    C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 8, None, 1.0, torch.ones(1, device="cuda"), None)
     assert torch.equal(before, p)
+    # ... and so does a non-finite gradient scale (= non-finite gradient norm upstream of the kernel)
+    for bad in (float("nan"), float("inf")):
+        C.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.01, 8, torch.tensor([bad], device="cuda"), 1.0, None, None)
+        assert torch.equal(before, p) and torch.equal(mb, m) and torch.equal(vb, v)
 
 
 def test_sumsq_and_pruning(C):
@@ -647,3 +653,104 @@ def test_producers_emit_the_same_e4m3_copy_as_the_standalone_quantiser(C):
     C.dropout_expand(a, ad, seed, [7], 0.1, q, inv, am)
     rq, ram = ref_q(a)
     assert torch.equal(q, rq) and float(am) == ram
+
+
+# ----------------------------------------------------------------------------------------- GPT-NeoX / Pythia leaf kernels
+@pytest.mark.parametrize("M,H,bias", [(300, 512, True), (257, 2048, True), (64, 768, False), (33, 1000, True)])
+def test_layernorm_fwd_bwd(F, M, H, bias):
+    torch.manual_seed(0)
+    x = (torch.randn(M, H, device="cuda") * 2 + 0.5).to(BF).requires_grad_()
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(BF).requires_grad_()
+    b = (0.1 * torch.randn(H, device="cuda")).to(BF).requires_grad_() if bias else None
+    dy = _rand(M, H)
+    y = F.layernorm(x, w, b, 1e-5)
+    y.backward(dy)
+    xf, wf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    bf = b.detach().float().requires_grad_() if bias else None
+    yf = torch.nn.functional.layer_norm(xf, (H,), wf, bf, 1e-5)
+    yf.backward(dy.float())
+    assert _relerr(y, yf) < 6e-3
+    assert _relerr(x.grad, xf.grad) < 8e-3 and _relerr(w.grad, wf.grad) < 8e-3
+    if bias:
+        assert _relerr(b.grad, bf.grad) < 8e-3
+
+
+@pytest.mark.parametrize("tanh_approx", [False, True])
+def test_gelu_fwd_bwd(F, tanh_approx):
+    torch.manual_seed(0)
+    z = (torch.randn(777, 264, device="cuda") * 2).to(BF).requires_grad_()
+    da = _rand(777, 264)
+    a = F.gelu(z, tanh_approx)
+    a.backward(da)
+    zf = z.detach().float().requires_grad_()
+    af = torch.nn.functional.gelu(zf, approximate="tanh" if tanh_approx else "none")
+    af.backward(da.float())
+    assert _relerr(a, af) < 5e-3 and _relerr(z.grad, zf.grad) < 6e-3
+
+
+@pytest.mark.parametrize("nh,hd,rot", [(8, 64, 16), (4, 128, 32), (2, 256, 64)])
+def test_neox_partial_rope(F, nh, hd, rot):
+    """In-place partial rotary on the fused query_key_value layout vs the reference expression (modeling_pythia.py:172-197)."""
+    from relora_b200.models.pythia import GPTNeoXRotaryEmbedding, apply_partial_rotary
+
+    torch.manual_seed(0)
+    B, T = 2, 37
+    qkv = _rand(B, T, nh, 3 * hd).requires_grad_()
+    rope = GPTNeoXRotaryEmbedding(rot, 128, device="cuda")
+    cos, sin = rope(qkv, seq_len=T)
+    out = F.neox_rope(qkv, cos[0, 0].float().contiguous(), sin[0, 0].float().contiguous(), nh, hd, rot)
+    g = _rand(B, T, nh, 3 * hd)
+    out.backward(g)
+    ref_in = qkv.detach().float().requires_grad_()
+    q = ref_in[..., :hd].permute(0, 2, 1, 3)
+    k = ref_in[..., hd:2 * hd].permute(0, 2, 1, 3)
+    pos = torch.arange(T, device="cuda").unsqueeze(0).expand(B, T)
+    qr, kr = apply_partial_rotary(q[..., :rot], k[..., :rot], cos.float(), sin.float(), pos)
+    qf = torch.cat((qr, q[..., rot:]), -1).permute(0, 2, 1, 3)
+    kf = torch.cat((kr, k[..., rot:]), -1).permute(0, 2, 1, 3)
+    want = torch.cat((qf, kf, ref_in[..., 2 * hd:]), -1)
+    want.backward(g.float())
+    assert _relerr(out, want) < 5e-3 and _relerr(qkv.grad, ref_in.grad) < 5e-3
+
+
+def test_pythia_native_leaf_ops_match_eager():
+    """Tiny Pythia on CUDA/bf16: LayerNorm / GELU / partial rotary / (head 64) attention kernels vs the same model forced onto the
+    PyTorch expressions (RELORA_B200_FORCE_REFERENCE semantics through ops.dispatch.force_reference)."""
+    from relora_b200.models import GPTNeoXForCausalLM, SimpleConfig
+    from relora_b200.ops import dispatch
+
+    torch.manual_seed(0)
+    cfg = SimpleConfig(model_type="gpt_neox", vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                       intermediate_size=1024, rotary_pct=0.25, max_position_embeddings=128, layer_norm_eps=1e-5,
+                       use_parallel_residual=True, hidden_act="gelu", rotary_emb_base=10000, tie_word_embeddings=False)
+    model = GPTNeoXForCausalLM(cfg).to("cuda", BF).train()
+    ids = torch.randint(0, 512, (2, 64), device="cuda")
+    out = model(input_ids=ids, labels=ids)
+    out.loss.backward()
+    g_native = {n: p.grad.float().clone() for n, p in model.named_parameters()}
+    model.zero_grad()
+    dispatch.force_reference(True)
+    try:
+        ref = model(input_ids=ids, labels=ids)
+        ref.loss.backward()
+    finally:
+        dispatch.force_reference(False)
+    assert abs(float(out.loss) - float(ref.loss)) < 3e-2
+    worst = max(_relerr(g_native[n], p.grad) for n, p in model.named_parameters() if p.grad is not None and float(p.grad.float().norm()) > 0)
+    assert worst < 0.08, worst
+
+
+def test_module_path_attention_uses_the_tcgen05_kernels(F):
+    """`F.causal_attention` (module path) vs torch SDPA on q, k, v [B, nh, T, hd] incl. the gradients."""
+    torch.manual_seed(0)
+    B, nh, T, hd = 2, 4, 200, 48
+    q, k, v = (_rand(B, nh, T, hd).requires_grad_() for _ in range(3))
+    do = _rand(B, nh, T, hd)
+    o = F.causal_attention(q, k, v)
+    o.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    of = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=True)
+    of.backward(do.float())
+    assert _relerr(o, of) < 1e-2
+    for a, b in ((q.grad, qf.grad), (k.grad, kf.grad), (v.grad, vf.grad)):
+        assert _relerr(a, b) < 2e-2
