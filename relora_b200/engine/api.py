@@ -97,11 +97,18 @@ class TrainingEngine:
         mean = total / ga
         self.last_local_loss = mean  # this rank's loss before the cross-rank mean (device scalar; bench.py's validity check)
         skip = torch.isnan(mean).float()
-        if dist.is_initialized() and dist.get_world_size() > 1:
-            pack = torch.stack([mean, skip])
-            dist.all_reduce(pack)
-            mean, skip = pack[0] / dist.get_world_size(), pack[1]
-        self.last_grad_norm = self.stepper.update(skip=skip).grad_norm
+        multi = dist.is_initialized() and dist.get_world_size() > 1
+        if multi and getattr(self.stepper, "folds_loss_reduce", False):
+            # the NVLink update combines [loss, NaN flag] over ranks in its norm exchange: no NCCL call on the step path
+            info = self.stepper.update(skip=skip, local_loss=mean)
+            mean = info.mean_loss
+        else:
+            if multi:
+                pack = torch.stack([mean, skip])
+                dist.all_reduce(pack)
+                mean, skip = pack[0] / dist.get_world_size(), pack[1]
+            info = self.stepper.update(skip=skip)
+        self.last_grad_norm = info.grad_norm
         # the fused / flat optimizers step inside update(); mark the wrapped torch counter so LambdaLR does not warn about order
         self.optimizer._opt_called = True
         self.scheduler.step()

@@ -680,24 +680,21 @@ class FusedLlamaStepper:
         self._loss_and_head_backward(False)
         return self.loss_out.clone()
 
+    @property
+    def folds_loss_reduce(self) -> bool:
+        """True when ``update(local_loss=...)`` combines loss / skip over ranks inside the NVLink kernel chain (no NCCL call)."""
+        return self.comm is not None
+
     @torch.no_grad()
-    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
+    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False,
+               local_loss: Optional[torch.Tensor] = None) -> UpdateInfo:
         opt = self.optimizer
         world = self.info.world_size
         if self.comm is not None:
-            grp = opt.param_groups[0]
-            opt.advance_step(skip)
-            norm = self.comm.fused_update(
-                grads_f32=self.store.grads, grad_buf=self.grad_buf, gred=self.gred, param_buf=self.param_buf,
-                exp_avg=opt.exp_avg, exp_avg_sq=opt.exp_avg_sq, n=self.store.numel, lr=grp["lr"], betas=grp["betas"],
-                eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=skip,
-                step_dev=opt._step_t)
-            total = norm[0].clone()
-            opt.undo_step_if_nonfinite(total, skip)
-            opt.zero_grad()
-            if error_if_nonfinite and not bool(torch.isfinite(total)):
-                raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
-            return UpdateInfo(total, False)
+            from .stepper import peer_memory_update
+
+            return peer_memory_update(self, grads_f32=self.store.grads, skip=skip, error_if_nonfinite=error_if_nonfinite,
+                                      local_loss=local_loss)
         grads = None
         if world > 1 and not self.sync.zero:
             # NCCL baseline: gradients cross the wire as bf16 (like the reference's bf16 DDP buckets), once per update

@@ -30,6 +30,10 @@ __all__ = ["UpdateInfo", "ModuleStepper", "trainable_named_parameters", "make_st
 class UpdateInfo:
     grad_norm: torch.Tensor  # device scalar (norm of the averaged gradient, before clipping)
     skipped: bool
+    # set by the peer-memory update when the caller handed it this rank's loss: mean loss over ranks and the number of ranks that
+    # asked to skip (device scalars; the reference's loss_info all-reduce folded into the kernel chain, torchrun_main.py:810)
+    mean_loss: Optional[torch.Tensor] = None
+    skip_count: Optional[torch.Tensor] = None
 
 
 def trainable_named_parameters(model: torch.nn.Module) -> List[Tuple[str, torch.nn.Parameter]]:
@@ -114,25 +118,16 @@ class ModuleStepper:
         return self.model(input_ids=input_ids, labels=input_ids).loss.detach()
 
     # ------------------------------------------------------------------ one optimizer update
+    @property
+    def folds_loss_reduce(self) -> bool:
+        """True when ``update(local_loss=...)`` combines loss / skip over ranks inside the NVLink kernel chain (no NCCL call)."""
+        return self.comm is not None
+
     @torch.no_grad()
-    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False) -> UpdateInfo:
+    def update(self, skip: Optional[torch.Tensor] = None, error_if_nonfinite: bool = False,
+               local_loss: Optional[torch.Tensor] = None) -> UpdateInfo:
         if self.comm is not None:
-            opt = self.optimizer
-            grp = opt.param_groups[0]
-            sk = None if skip is None else (skip if torch.is_tensor(skip) else torch.tensor(float(skip), device=self.store.device))
-            opt.advance_step(sk)
-            norm = self.comm.fused_update(
-                grads_f32=None, grad_buf=self.grad_buf, gred=self.gred, param_buf=self.param_buf, exp_avg=opt.exp_avg,
-                exp_avg_sq=opt.exp_avg_sq, n=self.store.numel, lr=grp["lr"], betas=grp["betas"], eps=grp["eps"],
-                weight_decay=grp["weight_decay"], step=opt.step_count, max_norm=self.clip, skip=sk, step_dev=opt._step_t)
-            total = norm[0].clone()
-            opt.undo_step_if_nonfinite(total, sk)
-            opt.zero_grad()
-            if error_if_nonfinite and not bool(torch.isfinite(total)):
-                raise RuntimeError(
-                    f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped."
-                )
-            return UpdateInfo(total, False)
+            return peer_memory_update(self, grads_f32=None, skip=skip, error_if_nonfinite=error_if_nonfinite, local_loss=local_loss)
         self.sync.reduce()
         total, scale = self.sync.grad_norm_and_scale(self.clip)
         if error_if_nonfinite and not bool(torch.isfinite(total)):
@@ -148,6 +143,32 @@ class ModuleStepper:
     def set_lr(self, lr: float) -> None:
         for g in self.optimizer.param_groups:
             g["lr"] = lr
+
+
+def peer_memory_update(st, *, grads_f32, skip, error_if_nonfinite: bool, local_loss) -> UpdateInfo:
+    """The data-parallel update on the hand-written NVLink kernels (``SymmComm.fused_update``), shared by both steppers: reduce-
+    scatter + Σg² → norm / loss / skip exchange → AdamW on the owned shard → parameter broadcast.  ``skip`` and ``local_loss`` are
+    this rank's values; a skip requested by any rank, or a non-finite gradient norm, leaves parameters, moments and the Adam step
+    count untouched on every rank."""
+    opt = st.optimizer
+    grp = opt.param_groups[0]
+    dev = st.store.device
+    sk = None if skip is None else (skip if torch.is_tensor(skip) else torch.tensor(float(skip), device=dev))
+    opt.advance_step(None)  # optimistic: taken back below when the kernels skipped
+    norm = st.comm.fused_update(
+        grads_f32=grads_f32, grad_buf=st.grad_buf, gred=st.gred, param_buf=st.param_buf, exp_avg=opt.exp_avg, exp_avg_sq=opt.exp_avg_sq,
+        n=st.store.numel, lr=grp["lr"], betas=grp["betas"], eps=grp["eps"], weight_decay=grp["weight_decay"], step=opt.step_count,
+        max_norm=st.clip, skip=sk, step_dev=opt._step_t, local_loss=local_loss)
+    total = norm[0].clone()
+    skip_count = st.comm.skip_all.clone()
+    skipped_dev = (skip_count > 0).to(torch.float32)
+    opt._step_t.sub_(skipped_dev)
+    opt.undo_step_if_nonfinite(total, skipped_dev)
+    opt.zero_grad()
+    if error_if_nonfinite and not bool(torch.isfinite(total)):
+        raise RuntimeError(f"The total norm of order 2.0 for gradients is non-finite ({float(total)}), so it cannot be clipped.")
+    mean_loss = st.comm.loss_out[0].clone() if local_loss is not None else None
+    return UpdateInfo(total, False, mean_loss=mean_loss, skip_count=skip_count)
 
 
 def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None):
