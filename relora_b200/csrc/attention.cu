@@ -213,9 +213,15 @@ __global__ void __launch_bounds__((4 * kFwdGroups + kFwdGroups) * 32, kFwdGroups
     // only raised -- and O rescaled by a TMEM load / multiply / store -- when a step's maximum exceeds it by more than
     // 2^8; any reference maximum is mathematically valid as long as exp2 stays in range, and the same m enters l.
     float m = kNegInf, l = 0.f;
+    // in-kernel clock64 trace (bench/attn_trace.py): compiled in only with -DRB_ATTN_TRACE -- even predicated off, its five
+    // stores + clock reads per step showed up as issue slots and `lg` stalls in the ncu source view of the production build
+#ifdef RB_ATTN_TRACE
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define ATR(slot) do { if (tr) p.trace[(slot) * 64 + jj] = clock64(); } while (0)
     if (tr) p.trace[7 * 64] = clock64();
+#else
+#define ATR(slot) do { } while (0)
+#endif
     for (int jj = 0; jj < n_kv; ++jj) {
       const int k0 = jj * BK;
       ATR(0);

@@ -962,6 +962,214 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
   }
 }
 
+// =============================================================================================
+// Two-kernel form of the LoRA input gradient with the frozen-path product supplied (`base`):
+//
+//   dx[M,N] = base[M,N] + inv_keep · Σ_g keep_g(row, col) ⊙ ( du_g[M,r] · A_g[r,N] )
+//
+// The products are tiny (K = r per group); the work is the epilogue (G TMEM reads + one mask hash per column pair and
+// group).  ncu on the single-epilogue-warpgroup version (lora_dx_kernel, Kb == 0): ~3950 instructions per thread and tile,
+// one warp per scheduler, 7.3 stall cycles per issue (barrier 2.1, long scoreboard 1.4, instruction fetch 1.3) -> 41.7 us for
+// M 12288 x N 768, G = 3 (0.17 of the HBM roofline).  Here TWO epilogue warpgroups split every 128-column tile into its two
+// 64-column slabs (two warps per scheduler, half the instructions each, independent slabs / named barriers / TMA stores).
+template <int G>
+__global__ void __launch_bounds__(384, 1)
+lora_dx_base_kernel(const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_out, const LoraDxArgs p) {
+  constexpr int BLOCK_N = 128;
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int kLoraStages = (G <= 2) ? 2 : 1;  // TMEM budget: kLoraStages · G · 128 <= 512 columns
+  constexpr uint32_t kTmemCols = 512;
+  static_assert(kLoraStages * G * BLOCK_N <= 512, "tensor memory budget");
+  static_assert(L::kSlabs >= 4, "two rotating slabs per epilogue warpgroup");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* lora_full = empty_bar + kStages;
+  uint64_t* lora_empty = lora_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(lora_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_du);
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&lora_full[a], 1);
+      mbar_init(&lora_empty[a], 256);  // both epilogue warpgroups release an accumulator stage
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_lora = p.r / BLOCK_K;
+
+  if (warp == 0) {
+    if (lane == 0) {  // TMA producer: du [M, G·r] K-major ; A [G·r, N] MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < G * kb_lora; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
+      int stage = 0, ls = 0;
+      uint32_t phase = 0, ls_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&lora_empty[ls], ls_phase ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g) {
+          const uint32_t d_tmem = tmem_base + (ls * G + g) * BLOCK_N;
+          for (int kb = 0; kb < kb_lora; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(kb == 0 && k == 0));
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(&lora_full[ls]);
+        if (++ls == kLoraStages) {
+          ls = 0;
+          ls_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================================================================== epilogue: warps 4-7 -> slab 0, warps 8-11 -> slab 1
+    const uint32_t quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const uint32_t half = (warp - kEpilogueWarp0) >> 2;     // 64-column slab of the tile handled by this warpgroup
+    const bool issuer = ((warp & 3) == 0) && lane == 0;     // one TMA-store issuer per warpgroup
+    uint8_t* stage_base = smem + L::kTileBytes + L::kBarrierBytes + half * 2 * L::kSlabBytes;  // two private rotating slabs
+    const uint32_t seed0 = p.seed_ptr ? *p.seed_ptr : 0u;
+    uint32_t seeds[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) seeds[g] = mix_seed(seed0, p.keys[g]);
+    int ls = 0;
+    uint32_t ls_phase = 0;
+    int slab_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N + half * 64;
+      const uint32_t rloc = quad * 32 + lane;
+      const uint32_t row = m0 + rloc;
+      const uint32_t rowmix = row * 0x9E3779B1u;
+      // this thread's 64 columns of the frozen-path product are requested now: the ~1 us global latency hides behind the MMAs
+      uint4 bpre[8];
+      {
+        const bool row_in = (int)row < p.M;
+        const bf16* bp = p.base + (long long)row * p.ld_base + n0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          bpre[q] = (row_in && n0 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + q * 8) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&lora_full[ls], ls_phase);
+      tc_fence_after();
+      uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
+      uint8_t* rowp = slab + rloc * 128;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t rr[G][16];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (ls * G + g) * BLOCK_N + half * 64 + c4 * 16), rr[g]);
+        tmem_ld_wait();
+        if (c4 == 3) {  // last read of the accumulators: hand them back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&lora_empty[ls]);
+        }
+        float cf[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf[i] = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint32_t sg = rowmix ^ seeds[g];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {  // one hash per column pair (common.cuh:keep_drop)
+            const uint32_t cp = (uint32_t)(n0 + c4 * 16 + i) >> 1;
+            const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
+            if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[g][i]);
+            if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[g][i + 1]);
+          }
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float f[8];
+          unpack8(bpre[c4 * 2 + h2], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(cf[h2 * 8 + i], p.inv_keep, f[i]);
+          const int q = c4 * 2 + h2;
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = pack8(f);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (issuer) {
+        if (n0 < p.N) {
+          tma_store_2d(&map_out, slab, n0, m0);
+          tma_store_commit();
+        }
+        tma_store_wait_read<1>();  // the slab used two tiles ago (the next one) has been read by its store
+      }
+      named_bar_sync(1 + half, 128);  // nobody overwrites the next slab before the issuer's wait returned
+      ++slab_counter;
+      if (++ls == kLoraStages) {
+        ls = 0;
+        ls_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: tensor-map construction (driver entry point resolved at run time; no link against libcuda)
 // ---------------------------------------------------------------------------------------------
@@ -1252,6 +1460,32 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   RB_CHECK_LAUNCH("lora_dx_kernel");
 }
 
+template <int G>
+static void launch_lora_dx_base(const LoraDxDesc& d, cudaStream_t stream) {
+  using L = SmemLayout<128>;
+  LoraDxArgs p;
+  p.M = d.M; p.N = d.N; p.Kb = 0; p.r = d.r;
+  p.base = reinterpret_cast<const bf16*>(d.base); p.ld_base = d.ld_base;
+  p.num_m_tiles = ceil_div(d.M, BLOCK_M);
+  p.num_n_tiles = ceil_div(d.N, 128);
+  p.thr16 = d.drop_threshold16; p.inv_keep = d.inv_keep; p.seed_ptr = d.seed_ptr;
+  for (int g = 0; g < 3; ++g) p.keys[g] = d.seed_key[g];
+  CUtensorMap m_du = make_map_2d(d.du, (long long)G * d.r, d.M, d.ld_du, BLOCK_K, BLOCK_M);
+  CUtensorMap m_a = make_map_2d(d.a, d.N, (long long)G * d.r, d.ld_a, 64, BLOCK_K);
+  CUtensorMap m_out = make_map_2d(d.out, d.N, d.M, d.ldc, 64, BLOCK_M);
+  auto kern = lora_dx_base_kernel<G>;
+  static bool configured = false;
+  if (!configured) {
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(lora_dx_base)");
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return;
+  launch_k(kern, grid, 384, L::kTotal, stream, m_du, m_a, m_out, p);
+  RB_CHECK_LAUNCH("lora_dx_base_kernel");
+}
+
 void lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   if (d.M <= 0 || d.N <= 0) return;
   if (d.groups < 1 || d.groups > 3) throw std::runtime_error("lora_dx: 1..3 stacked LoRA groups");
@@ -1259,6 +1493,16 @@ void lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   if (d.Kb == 0 && (d.base == nullptr || d.ld_base % 8 != 0 || (reinterpret_cast<uintptr_t>(d.base) & 15) != 0))
     throw std::runtime_error("lora_dx: Kb == 0 needs a 16-byte aligned base product");
   if (d.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) throw std::runtime_error("lora_dx: output must be 16-byte aligned");
+  static const bool split_epilogue = [] {
+    const char* e = getenv("RB_LORA_DX_BASE_SPLIT");  // 0: the single-warpgroup epilogue of lora_dx_kernel (diagnostics / A-B timing)
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (d.Kb == 0 && split_epilogue) {  // frozen-path product supplied: the two-warpgroup epilogue kernel
+    if (d.groups == 1) launch_lora_dx_base<1>(d, stream);
+    else if (d.groups == 2) launch_lora_dx_base<2>(d, stream);
+    else launch_lora_dx_base<3>(d, stream);
+    return;
+  }
   if (d.groups == 1) launch_lora_dx<1>(d, stream);
   else if (d.groups == 2) launch_lora_dx<2>(d, stream);
   else launch_lora_dx<3>(d, stream);

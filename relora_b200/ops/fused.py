@@ -319,7 +319,12 @@ def relora_linear_module(module, x: torch.Tensor) -> torch.Tensor:
 
         if module.lora_only:
             return module.lora_B(module.lora_A(module.lora_dropout(x))) * module._post_lora_scale()
-        out = F.linear(x, module.weight, module.bias)
+        if module.quantize is not None:
+            from ..relora.linear import packed_linear
+
+            out = packed_linear(x, module.qweight, module.bias)  # only the packed bytes are resident
+        else:
+            out = F.linear(x, module.weight, module.bias)
         pd = float(module.lora_dropout.p) if module.training else 0.0
         xd = x
         if pd > 0.0 and x.is_cuda:

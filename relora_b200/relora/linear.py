@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from ..obs import logger
 from ..ops import quant as _quant
 
-__all__ = ["ReLoRaLinear", "kaiming_bound"]
+__all__ = ["ReLoRaLinear", "kaiming_bound", "packed_linear"]
 
 
 def kaiming_bound(fan_in: int, a: float = math.sqrt(5)) -> float:
@@ -102,12 +102,12 @@ class ReLoRaLinear(nn.Module):
             if self.quantize is None:
                 self.weight = nn.Parameter(weight_data, requires_grad=False)
             else:
-                # keep a (frozen) parameter so state_dict round-trips in the reference layout;
-                # the packed copy is what the kernels consume and is refreshed on merge / load
-                self.weight = nn.Parameter(weight_data, requires_grad=False)
+                # ONLY the packed bytes + block scales are resident (like bitsandbytes' Params4bit / Int8Params upstream,
+                # relora.py:224-236): `self.weight` is no parameter but a transient dequantised view (see __getattr__), the
+                # forward / backward dequantise one layer at a time, and state_dict() still carries a `weight` entry so that
+                # checkpoints keep the reference layout
+                self._wdtype = weight_data.dtype
                 self.qweight = _quant.quantize(weight_data, self.quantize)
-                with torch.no_grad():
-                    self.weight.copy_(_quant.dequantize(self.qweight, self.weight.dtype))
 
         self.lora_A = _Factor(in_features, r, device=device, dtype=dtype)
         self.lora_B = _Factor(r, out_features, device=device, dtype=dtype)
@@ -128,20 +128,58 @@ class ReLoRaLinear(nn.Module):
         s = self._post_lora_scale()
         return float(s) if not torch.is_tensor(s) else float(s.detach().float().item())
 
-    def refresh_quantized(self):
-        """Re-pack ``weight`` after it changed (merge, checkpoint load)."""
-        if self.quantize is not None and self.weight is not None:
-            self.qweight = _quant.quantize(self.weight.data, self.quantize)
-            self.weight.data.copy_(_quant.dequantize(self.qweight, self.weight.dtype))
+    # ---- packed storage plumbing -------------------------------------------------------------------------------------
+    def __getattr__(self, name):
+        if name == "weight":
+            qw = self.__dict__.get("qweight")
+            if qw is not None:  # transient bf16 / fp32 view of the packed weight (never stored)
+                return _quant.dequantize(qw, self.__dict__.get("_wdtype", torch.float32))
+        return super().__getattr__(name)
 
-    def _load_from_state_dict(self, *args, **kwargs):
-        super()._load_from_state_dict(*args, **kwargs)
-        self.refresh_quantized()
+    def set_weight(self, value: torch.Tensor) -> None:
+        """Replace the frozen weight (merge, checkpoint load): re-packs when the storage is quantised."""
+        if self.quantize is not None:
+            self.qweight = _quant.quantize(value.detach(), self.quantize)
+        else:
+            self.weight.data.copy_(value.to(self.weight.dtype))
+
+    def frozen_weight_nbytes(self) -> int:
+        """Resident bytes of the frozen weight (packed data + scales, or the dense tensor)."""
+        if self.quantize is not None:
+            return int(self.qweight.nbytes)
+        return 0 if self.weight is None else int(self.weight.numel() * self.weight.element_size())
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if self.quantize is not None and self.qweight is not None:
+            destination[prefix + "weight"] = self.weight  # dequantised: checkpoints keep the reference key / dtype
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + "weight"
+        if self.quantize is not None and key in state_dict:
+            w = state_dict.pop(key)  # not a registered parameter: consume it here
+            try:
+                if tuple(w.shape) != (self.out_features, self.in_features):
+                    error_msgs.append(f"size mismatch for {key}: {tuple(w.shape)} vs {(self.out_features, self.in_features)}")
+                else:
+                    dev = self.qweight.data.device
+                    self.qweight = _quant.quantize(w.to(dev), self.quantize)
+                super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+            finally:
+                state_dict[key] = w
+            if key in unexpected_keys:
+                unexpected_keys.remove(key)
+            return
+        if self.quantize is not None and strict:
+            missing_keys.append(key)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
-        if self.qweight is not None and self.weight is not None:
-            self.qweight = self.qweight.to(self.weight.device)
+        if self.qweight is not None:
+            probe = fn(torch.empty(0, dtype=self._wdtype, device=self.qweight.data.device))  # where / what dtype do parameters go?
+            self._wdtype = probe.dtype if probe.is_floating_point() else self._wdtype
+            self.qweight = self.qweight.to(probe.device)
         return out
 
     # ------------------------------------------------------------------ merge
@@ -159,9 +197,13 @@ class ReLoRaLinear(nn.Module):
         if torch.is_tensor(scale):
             scale = scale.to(torch.float32)
         delta = (self.lora_B.weight.to(torch.float32) @ self.lora_A.weight.to(torch.float32)) * scale
-        merged = self.weight.data.to(torch.float32) + delta
-        self.weight.data.copy_(merged.to(self.weight.dtype))
-        self.refresh_quantized()
+        if self.quantize is not None:
+            # dequantise -> fp32 add -> requantise with fresh block scales (relora.py:277-299; the 8-bit branch is broken upstream)
+            merged = _quant.dequantize(self.qweight, torch.float32) + delta
+            self.qweight = _quant.quantize(merged, self.quantize)
+        else:
+            merged = self.weight.data.to(torch.float32) + delta
+            self.weight.data.copy_(merged.to(self.weight.dtype))
         self.reinit_lora(seed=seed, restart_index=restart_index, generator=generator)
 
     @torch.no_grad()
@@ -185,7 +227,10 @@ class ReLoRaLinear(nn.Module):
             return dispatch.lora_linear(self, x)
         if self.lora_only:
             return self.lora_B(self.lora_A(self.lora_dropout(x))) * self._post_lora_scale()
-        result = F.linear(x, self.weight, bias=self.bias)
+        if self.quantize is not None:
+            result = packed_linear(x, self.qweight, self.bias)
+        else:
+            result = F.linear(x, self.weight, bias=self.bias)
         result = result + self.lora_B(self.lora_A(self.lora_dropout(x))) * self._post_lora_scale()
         return result
 
@@ -195,6 +240,26 @@ class ReLoRaLinear(nn.Module):
             f"in_features={self.in_features}, out_features={self.out_features}, r={self.r}, "
             f"alpha={self.lora_alpha}, lora_only={self.lora_only}{q}"
         )
+
+
+class _PackedLinearFn(torch.autograd.Function):
+    """``y = x · dequant(W)ᵀ`` for a frozen block-scaled weight.  Neither forward nor backward keeps the dequantised matrix:
+    each builds the transient dense copy of ONE layer and drops it, so the resident frozen-weight memory is the packed size
+    (upstream: ``bnb.matmul_4bit`` / ``bnb.matmul`` on Params4bit / Int8Params, relora.py:314-317)."""
+
+    @staticmethod
+    def forward(ctx, x, qweight):
+        ctx.qweight = qweight
+        return F.linear(x, _quant.dequantize(qweight, x.dtype))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy @ _quant.dequantize(ctx.qweight, dy.dtype), None
+
+
+def packed_linear(x: torch.Tensor, qweight, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    y = _PackedLinearFn.apply(x, qweight)
+    return y if bias is None else y + bias
 
 
 def _warn_once(msg, _seen=set()):
