@@ -338,6 +338,69 @@ void swiglu_bwd(const Tensor& dh, const Tensor& gu, Tensor& dgu) {
   rb::swiglu_bwd(dh.data_ptr(), dh.stride(0), gu.data_ptr(), gu.stride(0), dgu.data_ptr(), dgu.stride(0), (int)dh.size(0), F, cur_stream());
 }
 
+// ---------------------------------------------------------------------------------------------- block-scaled MXFP8
+int64_t mx_sf_bytes(int64_t rows, int64_t k) { return rb::mx_sf_bytes(rows, k); }
+void mx_quantize_rows(const Tensor& x, Tensor& q, Tensor& sf) {
+  chk_bf16(x, "x"); chk_2d_rowmajor(x, "x");
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kByte && q.dim() == 2 && q.stride(1) == 1 && q.size(0) >= x.size(0), "q must be uint8 [M, Kpad]");
+  TORCH_CHECK(sf.is_cuda() && sf.scalar_type() == at::kByte && sf.is_contiguous() && sf.numel() >= rb::mx_sf_bytes(x.size(0), x.size(1)), "sf too small");
+  c10::cuda::CUDAGuard guard(x.device());
+  rb::mx_quantize_rows(x.data_ptr(), x.stride(0), q.data_ptr(), q.stride(0), sf.data_ptr(), (int)x.size(0), (int)x.size(1), cur_stream());
+}
+void mx_quantize_weight_2d(const OptTensor& w, const OptTensor& delta, Tensor& q, Tensor& sf_fwd, Tensor& sf_bwd, int64_t N, int64_t K) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kByte && q.dim() == 2 && q.stride(1) == 1, "q must be uint8 [Npad, Kpad]");
+  TORCH_CHECK(q.size(0) >= (N + 127) / 128 * 128 && q.size(1) >= (K + 127) / 128 * 128, "q must be padded to multiples of 128 in both dimensions");
+  TORCH_CHECK(sf_fwd.scalar_type() == at::kByte && sf_bwd.scalar_type() == at::kByte && sf_fwd.is_contiguous() && sf_bwd.is_contiguous());
+  TORCH_CHECK(sf_fwd.numel() >= rb::mx_sf_bytes(N, K) && sf_bwd.numel() >= rb::mx_sf_bytes(K, N), "scale buffers too small");
+  const void* wp = nullptr; long long ldw = 0;
+  if (w.has_value()) { chk_bf16(*w, "w"); chk_2d_rowmajor(*w, "w"); TORCH_CHECK(w->size(0) == N && w->size(1) == K); wp = w->data_ptr(); ldw = w->stride(0); }
+  const float* dp = nullptr; long long ldd = 0;
+  if (delta.has_value()) {
+    TORCH_CHECK(delta->scalar_type() == at::kFloat && delta->dim() == 2 && delta->stride(1) == 1 && delta->size(0) == N && delta->size(1) == K);
+    dp = delta->data_ptr<float>(); ldd = delta->stride(0);
+  }
+  c10::cuda::CUDAGuard guard(q.device());
+  rb::mx_quantize_weight_2d(wp, ldw, q.data_ptr(), sf_fwd.data_ptr(), dp, ldd, q.data_ptr(), q.stride(0), sf_fwd.data_ptr(), sf_bwd.data_ptr(),
+                            (int)N, (int)K, cur_stream());
+}
+void mx_dequantize_weight(const Tensor& q, const Tensor& sf_fwd, Tensor& out) {
+  chk_bf16(out, "out"); chk_2d_rowmajor(out, "out");
+  TORCH_CHECK(q.scalar_type() == at::kByte && q.dim() == 2 && q.stride(1) == 1 && sf_fwd.scalar_type() == at::kByte);
+  c10::cuda::CUDAGuard guard(q.device());
+  rb::mx_dequantize_weight(q.data_ptr(), q.stride(0), sf_fwd.data_ptr(), out.data_ptr(), out.stride(0), (int)out.size(0), (int)out.size(1), cur_stream());
+}
+void gemm_mx(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb, Tensor& out, int64_t M, int64_t N, int64_t K, bool b_mn_major,
+             const OptTensor& a2, const OptTensor& b2, const OptTensor& residual) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kByte && b.scalar_type() == at::kByte && a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte && sfa.is_contiguous() && sfb.is_contiguous());
+  chk_bf16(out, "out"); chk_2d_rowmajor(out, "out");
+  const int64_t Kpad = (K + 127) / 128 * 128;
+  TORCH_CHECK(a.size(0) >= M && a.size(1) >= Kpad, "a must be [>= M, >= Kpad] fp8 bytes");
+  if (b_mn_major) {
+    TORCH_CHECK(b.size(0) >= Kpad && b.size(1) >= N, "MN-major b must be [>= Kpad rows, >= N]");
+  } else {
+    TORCH_CHECK(b.size(0) >= N && b.size(1) >= Kpad, "K-major b must be [>= N, >= Kpad]");
+  }
+  TORCH_CHECK(sfa.numel() >= rb::mx_sf_bytes(M, K) && sfb.numel() >= rb::mx_sf_bytes(N, K), "scale buffers too small");
+  TORCH_CHECK(out.size(0) == M && out.size(1) == N);
+  rb::MxGemmDesc d;
+  d.a = a.data_ptr(); d.lda = a.stride(0); d.b = b.data_ptr(); d.ldb = b.stride(0); d.sfa = sfa.data_ptr(); d.sfb = sfb.data_ptr();
+  d.b_mn_major = b_mn_major; d.M = (int)M; d.N = (int)N; d.K = (int)K; d.out = out.data_ptr(); d.ldc = out.stride(0);
+  if (a2.has_value()) {
+    TORCH_CHECK(b2.has_value(), "a2 needs b2");
+    chk_bf16(*a2, "a2"); chk_bf16(*b2, "b2"); chk_2d_rowmajor(*a2, "a2"); chk_2d_rowmajor(*b2, "b2");
+    TORCH_CHECK(a2->size(0) == M && b2->size(0) == N && a2->size(1) == b2->size(1));
+    d.a2 = a2->data_ptr(); d.lda2 = a2->stride(0); d.b2 = b2->data_ptr(); d.ldb2 = b2->stride(0); d.K2 = (int)a2->size(1);
+  }
+  if (residual.has_value()) {
+    chk_bf16(*residual, "residual"); chk_2d_rowmajor(*residual, "residual");
+    TORCH_CHECK(residual->size(0) == M && residual->size(1) == N);
+    d.residual = residual->data_ptr(); d.ldr = residual->stride(0);
+  }
+  c10::cuda::CUDAGuard guard(a.device());
+  rb::gemm_mx(d, cur_stream());
+}
+
 // ---------------------------------------------------------------------------------------------- GPT-NeoX / Pythia block
 void layernorm_fwd(const Tensor& x, const Tensor& w, const OptTensor& b, Tensor& y, Tensor& mean, Tensor& rstd, double eps) {
   chk_bf16(x, "x"); chk_bf16(w, "weight"); chk_bf16(y, "y");
@@ -573,6 +636,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("swiglu_fwd", &swiglu_fwd, py::arg("gu"), py::arg("h"), py::arg("hd") = py::none(), py::arg("seed") = py::none(),
         py::arg("key") = 0, py::arg("p") = 0.0, py::arg("q8") = py::none(), py::arg("q_inv_scale") = py::none(), py::arg("q_amax") = py::none());
   m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("mx_sf_bytes", &mx_sf_bytes);
+  m.def("mx_quantize_rows", &mx_quantize_rows);
+  m.def("mx_quantize_weight_2d", &mx_quantize_weight_2d);
+  m.def("mx_dequantize_weight", &mx_dequantize_weight);
+  m.def("gemm_mx", &gemm_mx, py::arg("a"), py::arg("sfa"), py::arg("b"), py::arg("sfb"), py::arg("out"), py::arg("M"), py::arg("N"), py::arg("K"),
+        py::arg("b_mn_major") = false, py::arg("a2") = py::none(), py::arg("b2") = py::none(), py::arg("residual") = py::none());
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("gelu_fwd", &gelu_fwd);

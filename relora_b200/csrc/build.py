@@ -27,7 +27,7 @@ PKG = os.path.dirname(HERE)
 BUILD_DIR = os.path.join(HERE, "_build")
 TARGET = os.path.join(PKG, "_C.so")
 
-CUDA_SOURCES = ["gemm_tcgen05.cu", "elementwise.cu", "norm_warp.cu", "rope.cu", "optim.cu", "loss.cu", "attention.cu", "fp8.cu", "comm.cu", "neox.cu"]
+CUDA_SOURCES = ["gemm_tcgen05.cu", "elementwise.cu", "norm_warp.cu", "rope.cu", "optim.cu", "loss.cu", "attention.cu", "fp8.cu", "comm.cu", "neox.cu", "gemm_mx.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 HEADERS = ["common.cuh", "sm100.cuh", "gemm.h", "tensormap.h", "fp8out.h", "kernels.h", "attention.h", "comm.h"]
 

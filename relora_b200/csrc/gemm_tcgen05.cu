@@ -1276,6 +1276,11 @@ CUtensorMap make_map_3d_bf16(const void* ptr, long long d0, long long d1, long l
   return m;
 }
 
+// exported for the other translation units (gemm_mx.cu): same cache, same checks
+CUtensorMap make_map_2d_sw128(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int esize) {
+  return make_map_2d(ptr, inner, outer, ld, box_inner, box_outer, esize);
+}
+
 // Operand covering `mn` rows/cols of the output dimension and `k` of the reduction dimension.
 static CUtensorMap operand_map(const Operand& o, long long mn, long long k, int block_mn, bool fp8 = false) {
   if (fp8) return make_map_2d(o.ptr, k, mn, o.ld, 2 * BLOCK_K, block_mn, 1);  // E4M3 bytes, K-major only

@@ -65,6 +65,33 @@ void gelu_bwd(const void* da, const void* z, void* dz, long long n, bool tanh_ap
 void neox_rope(void* qkv, long long ld, long long rows, int T, int nh, int hd, int rot, const float* cos, const float* sin, int pos0,
                bool inverse, cudaStream_t s);
 
+// ---- block-scaled MXFP8 path (gemm_mx.cu) ------------------------------------------------------
+// Scale factors live in [row block of 128][group of 128 reduction elements][512 bytes] blocks (the tcgen05.cp / MMA layout).
+long long mx_sf_bytes(long long rows, long long k_elems);
+// x bf16 [M, K] (pitch ldx) -> E4M3 q [M, Kpad] (pitch ldq >= Kpad = K rounded up to 128, padding written as zero) + UE8M0 scales per (row, 32 cols)
+void mx_quantize_rows(const void* x, long long ldx, void* q, long long ldq, void* sf, int M, int K, cudaStream_t s);
+// W [N, K] -> E4M3 q (pitch ldq >= Kpad, Npad rows allocated) with ONE scale per 32 x 32 tile, written in the forward layout (rows N, reduction K)
+// and in the backward layout (rows K, reduction N).  Source: bf16 `w` (pitch ldw), or -- w == nullptr -- the packed q_old / sf_old (may
+// alias q / sf_fwd: requantisation in place); `delta` (fp32 [N, K], pitch ldd, nullable) is added before quantising (the ReLoRA merge).
+void mx_quantize_weight_2d(const void* w, long long ldw, const void* q_old, const void* sf_old, const float* delta, long long ldd, void* q,
+                           long long ldq, void* sf_fwd, void* sf_bwd, int N, int K, cudaStream_t s);
+void mx_dequantize_weight(const void* q, long long ldq, const void* sf_fwd, void* out, long long ldo, int N, int K, cudaStream_t s);
+// out[M,N] (bf16) = A8[M,K]·B8ᵀ (block-scaled E4M3, kind::mxf8f6f4) + A2[M,K2]·B2[N,K2]ᵀ (bf16, same accumulator) (+ residual)
+struct MxGemmDesc {
+  const void *a = nullptr, *b = nullptr;   // fp8 bytes; a [M, Kpad] K-major; b [N, Kpad] K-major, or (b_mn_major) [Kpad rows, N] as stored
+  long long lda = 0, ldb = 0;
+  const void *sfa = nullptr, *sfb = nullptr;
+  bool b_mn_major = false;
+  const void *a2 = nullptr, *b2 = nullptr; // bf16 K-major LoRA segment (optional)
+  long long lda2 = 0, ldb2 = 0;
+  int M = 0, N = 0, K = 0, K2 = 0;
+  void* out = nullptr;
+  long long ldc = 0;
+  const void* residual = nullptr;
+  long long ldr = 0;
+};
+void gemm_mx(const MxGemmDesc& d, cudaStream_t stream);
+
 // ---- embedding -----------------------------------------------------------------------------
 void embedding_fwd(const int64_t* ids, const void* table, void* out, int M, int H, cudaStream_t s);
 // dtable_f32[ids[m], :] += dout[m, :]   (skips padding_idx)

@@ -540,6 +540,12 @@ def run(args) -> dict:
                 seed=args.seed,
                 reset_index=st.n_optimizer_resets,
             )
+            from ..utils import check_lr_and_alert, optimizer_state_size
+
+            # after a reset the schedule must be at (nearly) zero lr; a large value means reset and schedule are out of phase
+            check_lr_and_alert(optimizer, max_lr=0.05 * args.lr + 1e-12, sink=sink if rank == 0 else None, step=st.global_step)
+            sz = optimizer_state_size(optimizer)
+            logger.info(f"Optimizer state after reset: {sz['exp_avg_nonzero'] / 1e6:.2f}M / {sz['exp_avg_numel'] / 1e6:.2f}M non-zero first moments")
         if can_reset_optimizer and rel % args.cycle_length == 2:
             logger.info(f"First step after optimizer reset lr is {optimizer.param_groups[0]['lr']}")
 

@@ -202,3 +202,42 @@ def test_reference_relora_state_dict_interchange(reference_modules):
     for (n, p), (n2, p2) in zip(ref_w.wrapped_model.named_parameters(), ours.wrapped_model.named_parameters()):
         if n.endswith("q_proj.weight") or n.endswith("down_proj.weight"):
             assert torch.allclose(p, p2, atol=1e-6), n
+
+
+def test_utils_state_size_lr_alarm_and_packed_bytes():
+    from relora_b200.utils import check_lr_and_alert, frozen_weight_bytes, optimizer_state_size
+
+    torch.manual_seed(0)
+    p = [torch.nn.Parameter(torch.randn(16, 8)) for _ in range(2)]
+    opt = torch.optim.AdamW(p, lr=1e-3)
+    for q in p:
+        q.grad = torch.randn_like(q)
+    opt.step()
+    s = optimizer_state_size(opt)
+    assert s["exp_avg_numel"] == 256 and s["exp_avg_nonzero"] == 256
+
+    class Sink:
+        def __init__(self):
+            self.alerts = []
+
+        def alert(self, title, text):
+            self.alerts.append((title, text))
+
+    sink = Sink()
+    assert not check_lr_and_alert(opt, max_lr=1e-2, sink=sink)
+    assert check_lr_and_alert(opt, max_lr=1e-4, sink=sink) and len(sink.alerts) == 1
+    # block-scaled storage really shrinks the resident frozen weight: mxfp8 = 1 + 1/32 bytes, nvfp4 = 1/2 + 1/16 bytes per element
+    for fmt, ratio in (("mxfp8", (1 + 1 / 32) / 2), ("nvfp4", (0.5 + 1 / 16) / 2)):
+        lin = ReLoRaLinear(256, 128, r=8, bias=False, weight_data=torch.randn(128, 256) * 0.02, quantize=fmt)
+        b = frozen_weight_bytes(torch.nn.Sequential(lin))
+        assert abs(b["resident_bytes"] / b["bf16_bytes"] - ratio) < 0.01, (fmt, b)
+        assert "weight" not in dict(lin.named_parameters())          # no dense copy is resident ...
+        sd = lin.state_dict()
+        assert sd["weight"].shape == (128, 256)                      # ... but checkpoints keep the reference key
+        lin2 = ReLoRaLinear(256, 128, r=8, bias=False, quantize=fmt)
+        lin2.load_state_dict(sd)
+        assert float((lin2.weight - lin.weight).norm() / lin.weight.norm()) < (0.02 if fmt == "mxfp8" else 0.12)  # requantisation is near-idempotent
+        x = torch.randn(4, 256, requires_grad=True)
+        y = lin(x)
+        y.sum().backward()
+        assert x.grad is not None and torch.isfinite(x.grad).all()
