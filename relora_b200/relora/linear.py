@@ -133,13 +133,24 @@ class ReLoRaLinear(nn.Module):
         if name == "weight":
             qw = self.__dict__.get("qweight")
             if qw is not None:  # transient bf16 / fp32 view of the packed weight (never stored)
-                return _quant.dequantize(qw, self.__dict__.get("_wdtype", torch.float32))
+                return _dequantize_any(qw, self.__dict__.get("_wdtype", torch.float32))
         return super().__getattr__(name)
+
+    def _pack(self, value: torch.Tensor):
+        """Packed form of ``value``: on CUDA, ``mxfp8`` uses the tensor-core layout of csrc/gemm_mx.cu (E4M3 + one UE8M0 scale per
+        32 x 32 tile, read by ``tcgen05.mma.kind::mxf8f6f4.block_scale`` in forward and input gradient); everything else (CPU, nvfp4) the
+        reference layout of ops/quant.py."""
+        if self.quantize == "mxfp8" and value.is_cuda:
+            from ..ops import mx, native
+
+            if native.available() and mx.supported(self.out_features, self.in_features):
+                return mx.quantize_weight(value.detach())
+        return _quant.quantize(value.detach(), self.quantize)
 
     def set_weight(self, value: torch.Tensor) -> None:
         """Replace the frozen weight (merge, checkpoint load): re-packs when the storage is quantised."""
         if self.quantize is not None:
-            self.qweight = _quant.quantize(value.detach(), self.quantize)
+            self.qweight = self._pack(value)
         else:
             self.weight.data.copy_(value.to(self.weight.dtype))
 
@@ -162,8 +173,8 @@ class ReLoRaLinear(nn.Module):
                 if tuple(w.shape) != (self.out_features, self.in_features):
                     error_msgs.append(f"size mismatch for {key}: {tuple(w.shape)} vs {(self.out_features, self.in_features)}")
                 else:
-                    dev = self.qweight.data.device
-                    self.qweight = _quant.quantize(w.to(dev), self.quantize)
+                    dev = _device_of(self.qweight)
+                    self.qweight = self._pack(w.to(dev))
                 super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
             finally:
                 state_dict[key] = w
@@ -177,9 +188,16 @@ class ReLoRaLinear(nn.Module):
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         if self.qweight is not None:
-            probe = fn(torch.empty(0, dtype=self._wdtype, device=self.qweight.data.device))  # where / what dtype do parameters go?
+            cur = _device_of(self.qweight)
+            probe = fn(torch.empty(0, dtype=self._wdtype, device=cur))  # where / what dtype do parameters go?
             self._wdtype = probe.dtype if probe.is_floating_point() else self._wdtype
-            self.qweight = self.qweight.to(probe.device)
+            if probe.device != cur:
+                if probe.device.type != cur.type:
+                    # CPU <-> CUDA: the packed layout changes with the device (reference layout vs tensor-core layout), so re-pack
+                    # from the dequantised values once (a one-time requantisation, not a per-step cost)
+                    self.qweight = self._pack(_dequantize_any(self.qweight, torch.float32).to(probe.device))
+                else:
+                    self.qweight = self.qweight.to(probe.device)
         return out
 
     # ------------------------------------------------------------------ merge
@@ -199,8 +217,13 @@ class ReLoRaLinear(nn.Module):
         delta = (self.lora_B.weight.to(torch.float32) @ self.lora_A.weight.to(torch.float32)) * scale
         if self.quantize is not None:
             # dequantise -> fp32 add -> requantise with fresh block scales (relora.py:277-299; the 8-bit branch is broken upstream)
-            merged = _quant.dequantize(self.qweight, torch.float32) + delta
-            self.qweight = _quant.quantize(merged, self.quantize)
+            if not isinstance(self.qweight, _quant.QuantizedWeight):
+                from ..ops import mx
+
+                mx.merge_(self.qweight, delta)  # one kernel, in place on the packed bytes
+            else:
+                merged = _quant.dequantize(self.qweight, torch.float32) + delta
+                self.qweight = _quant.quantize(merged, self.quantize)
         else:
             merged = self.weight.data.to(torch.float32) + delta
             self.weight.data.copy_(merged.to(self.weight.dtype))
@@ -242,6 +265,18 @@ class ReLoRaLinear(nn.Module):
         )
 
 
+def _device_of(qw) -> torch.device:
+    return (qw.data if isinstance(qw, _quant.QuantizedWeight) else qw.q).device
+
+
+def _dequantize_any(qw, dtype) -> torch.Tensor:
+    if isinstance(qw, _quant.QuantizedWeight):
+        return _quant.dequantize(qw, dtype)
+    from ..ops import mx
+
+    return mx.dequantize_weight(qw, dtype)
+
+
 class _PackedLinearFn(torch.autograd.Function):
     """``y = x · dequant(W)ᵀ`` for a frozen block-scaled weight.  Neither forward nor backward keeps the dequantised matrix:
     each builds the transient dense copy of ONE layer and drops it, so the resident frozen-weight memory is the packed size
@@ -258,6 +293,10 @@ class _PackedLinearFn(torch.autograd.Function):
 
 
 def packed_linear(x: torch.Tensor, qweight, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if not isinstance(qweight, _quant.QuantizedWeight):
+        from ..ops import mx
+
+        return mx.linear(x, qweight, bias)  # block-scaled tensor-core GEMMs on the packed bytes (forward and input gradient)
     y = _PackedLinearFn.apply(x, qweight)
     return y if bias is None else y + bias
 
