@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
       unpack8(t ? g1 : g0, g);
       unpack8(t ? u1 : u0, u);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
+      for (int j = 0; j < 8; ++j) o[j] = __fdividef(g[j], 1.f + __expf(-g[j])) * u[j];  // MUFU.EX2 + MUFU.RCP, no IEEE division sequence
       const bf16x8 packed = pack8(o);
       *reinterpret_cast<bf16x8*>(h + row * ldh + c) = packed;
       if (f8.q != nullptr) {
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
     unpack8(*reinterpret_cast<const bf16x8*>(dh + row * lddh + c), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float sg = 1.f / (1.f + __expf(-g[j]));
+      const float sg = __fdividef(1.f, 1.f + __expf(-g[j]));
       const float silu = g[j] * sg;
       du[j] = d[j] * silu;
       dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));

@@ -962,6 +962,253 @@ lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant
   }
 }
 
+// One-kernel form (frozen-path product in the same kernel, Kb > 0) with TWO epilogue warpgroups, one per 64-column half of the tile.
+template <int G>
+__global__ void __launch_bounds__(384, 1)
+lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_a,
+               const __grid_constant__ CUtensorMap map_out, const LoraDxArgs p) {
+  constexpr int BLOCK_N = 128;
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int kBaseStages = (G <= 2) ? 2 : 1;  // TMEM budget: (kBaseStages + kLoraStages·G) · 128 <= 512 columns
+  constexpr int kLoraStages = (G == 1) ? 2 : 1;
+  constexpr uint32_t kTmemCols = 512;
+  static_assert((kBaseStages + kLoraStages * G) * BLOCK_N <= 512, "tensor memory budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* lora_full = empty_bar + kStages;
+  uint64_t* lora_empty = lora_full + 2;
+  uint64_t* base_full = lora_empty + 2;
+  uint64_t* base_empty = base_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(base_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_du);
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&lora_full[a], 1);
+      mbar_init(&lora_empty[a], 256);
+      mbar_init(&base_full[a], 1);
+      mbar_init(&base_empty[a], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_lora = p.r / BLOCK_K;                     // r is a multiple of 64
+  const int kb_base = (p.Kb + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < G * kb_lora; ++kb) {  // du [M, G·r] K-major ; A [G·r, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          advance();
+        }
+        for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          load_operand<BLOCK_M, false>(&map_dy, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+          load_operand<BLOCK_N, true>(&map_w, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ls = 0, bs = 0;
+      uint32_t ls_phase = 0, bs_phase = 0;
+      auto mma_block = [&](uint32_t d_tmem, bool first) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(first && k == 0));
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&lora_empty[ls], ls_phase ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g) {
+          const uint32_t d_tmem = tmem_base + (kBaseStages + ls * G + g) * BLOCK_N;
+          for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
+        }
+        umma_commit(&lora_full[ls]);
+        if (kb_base > 0) {
+          mbar_wait(&base_empty[bs], bs_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
+          for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
+          umma_commit(&base_full[bs]);
+        }
+        if (++ls == kLoraStages) {
+          ls = 0;
+          ls_phase ^= 1;
+        }
+        if (++bs == kBaseStages) {
+          bs = 0;
+          bs_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================================================================== epilogue: warps 4-7 -> columns 0-63, warps 8-11 -> 64-127
+    // (the single-warpgroup epilogue was ~3x longer than the tile's MMAs at K = 768: ncu, profiles/ncu/lora_dx_k2560_g1_round2)
+    const uint32_t quad = warp & 3;
+    const uint32_t half = (warp - kEpilogueWarp0) >> 2;
+    const bool issuer = ((warp & 3) == 0) && lane == 0;
+    uint8_t* stage_base = smem + L::kTileBytes + L::kBarrierBytes + half * 2 * L::kSlabBytes;  // two private rotating slabs
+    const uint32_t seed0 = p.seed_ptr ? *p.seed_ptr : 0u;
+    uint32_t seeds[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) seeds[g] = mix_seed(seed0, p.keys[g]);
+    int ls = 0, bs = 0;
+    uint32_t ls_phase = 0, bs_phase = 0;
+    int slab_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N + half * 64;
+      const uint32_t rloc = quad * 32 + lane;
+      const uint32_t row = m0 + rloc;
+      const uint32_t rowmix = row * 0x9E3779B1u;
+      // ---- phase 1: masked sum of this half's LoRA accumulator columns, packed to bf16x2 (overlaps the frozen-path MMAs)
+      uint32_t cpk[32];
+      mbar_wait(&lora_full[ls], ls_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float cf[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf[i] = 0.f;
+        uint32_t rr[G][16];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + half * 64 + c4 * 16), rr[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint32_t sg = rowmix ^ seeds[g];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {  // one hash per column pair (common.cuh:keep_drop)
+            const uint32_t cp = (uint32_t)(n0 + c4 * 16 + i) >> 1;
+            const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
+            if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[g][i]);
+            if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[g][i + 1]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cpk[c4 * 8 + i] = pack_bf16x2(cf[2 * i] * p.inv_keep, cf[2 * i + 1] * p.inv_keep);
+      }
+      tc_fence_before();
+      mbar_arrive(&lora_empty[ls]);
+      // ---- phase 2: frozen-path accumulator (this half's 64 columns) + combined LoRA term -> bf16 slab -> TMA store
+      mbar_wait(&base_full[bs], bs_phase);
+      tc_fence_after();
+      uint8_t* slab = stage_base + (slab_counter & 1) * L::kSlabBytes;
+      uint8_t* rowp = slab + rloc * 128;
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + half * 64), r0);
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + half * 64 + 32), r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&base_empty[bs]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float2 c2 = unpack_bf16x2(cpk[q * 4 + i / 2]);
+            const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+            const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
+            f[i] = __uint_as_float(raw0) + c2.x;
+            f[i + 1] = __uint_as_float(raw1) + c2.y;
+          }
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = pack8(f);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (issuer) {
+        if (n0 < p.N) {
+          tma_store_2d(&map_out, slab, n0, m0);
+          tma_store_commit();
+        }
+        tma_store_wait_read<1>();
+      }
+      named_bar_sync(1 + half, 128);
+      ++slab_counter;
+      if (++ls == kLoraStages) {
+        ls = 0;
+        ls_phase ^= 1;
+      }
+      if (++bs == kBaseStages) {
+        bs = 0;
+        bs_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // =============================================================================================
 // Two-kernel form of the LoRA input gradient with the frozen-path product supplied (`base`):
 //
@@ -1452,15 +1699,30 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
     m_dy = make_map_2d(d.dy, d.Kb, d.M, d.ld_dy, BLOCK_K, BLOCK_M);
     m_w = make_map_2d(d.w, d.N, d.Kb, d.ld_w, 64, BLOCK_K);
   }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return;
+  static const bool split = [] {
+    const char* e = getenv("RB_LORA_DX_SPLIT");  // 0: single epilogue warpgroup (the round-1 kernel; A/B timing)
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (d.Kb > 0 && split) {
+    auto kern2 = lora_dx_fused2_kernel<G>;
+    static bool configured2 = false;
+    if (!configured2) {
+      check(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(lora_dx_fused2)");
+      configured2 = true;
+    }
+    launch_k(kern2, grid, 384, L::kTotal, stream, m_dy, m_w, m_du, m_a, m_out, p);
+    RB_CHECK_LAUNCH("lora_dx_fused2_kernel");
+    return;
+  }
   auto kern = lora_dx_kernel<G>;
   static bool configured = false;
   if (!configured) {
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(lora_dx)");
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (grid <= 0) return;
   launch_k(kern, grid, kNumThreads, L::kTotal, stream, m_dy, m_w, m_du, m_a, m_out, p);
   RB_CHECK_LAUNCH("lora_dx_kernel");
 }

@@ -41,6 +41,20 @@ def broadcast_params(module: torch.nn.Module, src: int = 0) -> None:
             continue
         seen.add(base.data_ptr())
         dist.broadcast(base, src=src)
+    # block-scaled frozen weights are neither parameters nor buffers (packed bytes + scales): replicate them as well
+    for m in module.modules():
+        qw = getattr(m, "__dict__", {}).get("qweight")
+        if qw is None:
+            continue
+        for name in ("q", "sf_fwd", "sf_bwd", "data", "scales", "tensor_scale"):
+            t = getattr(qw, name, None)
+            if torch.is_tensor(t) and t.numel() > 0:
+                if t.dim() == 0:
+                    buf = t.reshape(1).clone()
+                    dist.broadcast(buf, src=src)
+                    t.copy_(buf[0])
+                else:
+                    dist.broadcast(t, src=src)
 
 
 class GradSync:

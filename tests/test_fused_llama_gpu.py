@@ -195,3 +195,31 @@ def test_cli_end_to_end_on_the_fused_executor(tmp_path, extra):
     # autoresume picks up the last checkpoint and continues to a longer horizon
     res2 = main(args + ["--autoresume", "true", "--num_training_steps", "12"])
     assert res2["update_step"] == 12 and "model_12" in os.listdir(d)
+
+
+@pytest.mark.parametrize("quant", ["8bit", "4bit"])
+def test_cli_quantized_frozen_weights_train_on_packed_storage(tmp_path, quant):
+    """`--quantize 8bit|4bit` (reference: bitsandbytes int8 / NF4, relora.py:222-238): the frozen weights are resident only as packed
+    bytes + block scales; 8bit runs the block-scaled MXFP8 tensor-core GEMMs (csrc/gemm_mx.cu), a merge requantises in place, and the
+    checkpoint keeps the reference layout (dense `weight` entries)."""
+    import json
+    import os
+
+    from torchrun_main import main
+
+    cfg = {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "vocab_size": 4096, "hidden_size": 256, "intermediate_size": 512,
+           "num_hidden_layers": 2, "num_attention_heads": 4, "rms_norm_eps": 1e-6, "max_sequence_length": 256, "hidden_act": "silu",
+           "bos_token_id": 0, "eos_token_id": 1, "pad_token_id": -1, "initializer_range": 0.02, "use_cache": True}
+    cfg_path = str(tmp_path / "llama_tiny.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    d = str(tmp_path / "run")
+    args = ["--model_config", cfg_path, "--synthetic_data", "4096", "--batch_size", "4", "--total_batch_size", "8", "--max_length", "128",
+            "--lr", "1e-3", "--use_peft", "--lora_r", "128", "--relora", "4", "--cycle_length", "4", "--restart_warmup_steps", "1",
+            "--scheduler", "cosine_restarts", "--warmup_steps", "2", "--num_training_steps", "8", "--save_every", "8",
+            "--eval_every", "100", "--save_dir", d, "--dtype", "bfloat16", "--workers", "0", "--init_lora_a", "kaiming", "--quantize", quant]
+    res = main(args)
+    assert res["executor"] == "ModuleStepper" and res["update_step"] == 8 and res["n_lora_restarts"] == 1
+    assert torch.isfinite(torch.tensor(res["final_eval_loss"])) and res["final_eval_loss"] < 9.0
+    sd = torch.load(os.path.join(d, "model_8", "pytorch_model.bin"), weights_only=True)
+    w = sd["model.layers.0.self_attn.q_proj.weight"]
+    assert w.shape == (256, 256) and bool(torch.isfinite(w.float()).all())
