@@ -94,6 +94,29 @@ __device__ __forceinline__ void ld64(uint32_t taddr, float* v) {  // 64 fp32 col
   }
 }
 
+__device__ __forceinline__ void ld32(uint32_t taddr, float* v) {  // 32 fp32 columns of this thread's TMEM lane
+  uint32_t a[32];
+  tmem_ld_32x32b_x32(taddr, a);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
+}
+// half `hf` (32 values = 4 chunks of 8) of row `r` of a [128 x 64] bf16 tile (128-byte swizzle)
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int hf, const float* v) {
+  uint8_t* rowp = tile + r * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v[q * 8 + i];
+    *reinterpret_cast<uint4*>(rowp + (((hf * 4 + q) ^ (r & 7)) << 4)) = pack8(f);
+  }
+}
+// The backward kernels have no row reductions (lse and delta are inputs), so TWO warps share every row: warp w and w + 4 own
+// the same TMEM lanes and split the 64 columns of a step.  Halves the per-thread work of the S / dP -> dS dependency chain
+// that bounds these kernels (ncu round 2: 15 % warps active, 60 % of the stall samples waiting on the chain).
+constexpr int kBwdRowWarps = 8;
+
 struct FwdArgs {
   long long* trace;  // diagnostics: clock64 stamps of the heaviest CTA (bench/attn_trace.py); normally null
   bf16* out;
@@ -362,13 +385,13 @@ struct BwdArgs {
 };
 
 // =============================================================================================== backward: dQ
-__global__ void __launch_bounds__((4 * kDqGroups + kDqGroups) * 32, kDqGroups == 1 ? 2 : 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__((kBwdRowWarps * kDqGroups + kDqGroups) * 32, kDqGroups == 1 ? 2 : 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                    const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
   constexpr int NG = kDqGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) pdl_launch_dependents();
-  const bool is_ctrl = warp >= 4 * NG;
-  const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
+  const bool is_ctrl = warp >= kBwdRowWarps * NG;
+  const int g = is_ctrl ? warp - kBwdRowWarps * NG : warp / kBwdRowWarps;  // group of this warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem = smem0 + g * kDqGroupBytes;
@@ -404,13 +427,13 @@ __global__ void __launch_bounds__((4 * kDqGroups + kDqGroups) * 32, kDqGroups ==
       mbar_init(&kv_free[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(ds_ready, 128);
+    mbar_init(ds_ready, 32 * kBwdRowWarps);
     mbar_init(dq_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
   }
-  if (warp == 4 * NG) {
+  if (warp == kBwdRowWarps * NG) {
     tmem_alloc(tmem_slot, pow2_cols(NG * 256));  // per group (256 columns): S 0-63, dP 64-127, dQ 128-191
     tmem_relinquish();
   }
@@ -469,42 +492,42 @@ __global__ void __launch_bounds__((4 * kDqGroups + kDqGroups) * 32, kDqGroups ==
       }
     }
   } else {
-    const int r = threadIdx.x & 127;
+    const int r = threadIdx.x & 127, hf = (threadIdx.x >> 7) & 1;  // row of the query block, column half of every step
     const int t = t0 + r;
-    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, 0);
+    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, hf * 32);
     const long long stat = ((long long)b * p.nh + head) * p.T + t;
     const float lse = (active && t < p.T) ? p.lse[stat] : 0.f;
     const float dl = (active && t < p.T) ? p.delta[stat] : 0.f;
     for (int jj = 0; jj < n_kv; ++jj) {
-      const int k0 = jj * BK;
+      const int k0 = jj * BK + hf * 32;
       attn_wait(sdp_full, jj & 1);
       tc_fence_after();
-      float s[64], dp[64];
-      ld64(lane_addr, s);
-      ld64(lane_addr + 64, dp);
-      const bool edge = (k0 + BK - 1 > t0) || (k0 + BK > p.T);
+      float s[32], dp[32];
+      ld32(lane_addr, s);
+      ld32(lane_addr + 64, dp);
+      const bool edge = (jj * BK + BK - 1 > t0) || (jj * BK + BK > p.T);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int c = 0; c < 32; ++c) {
         float pr = fast_exp2(fmaf(s[c], p.scale_log2, -lse));
         if (edge && (k0 + c > t || k0 + c >= p.T)) pr = 0.f;
         s[c] = pr * (dp[c] - dl) * p.scale;
       }
-      store_row64(sdS, r, s);
+      store_row32(sdS, r, hf, s);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
     }
-    float dq[64];
+    float dq[32];
     if (active) {
       attn_wait(dq_full, 0);
       tc_fence_after();
-      ld64(lane_addr + 128, dq);
+      ld32(lane_addr + 128, dq);
     }
     if (active && t < p.T) {
-      bf16* op = p.dqkv + (long long)(row0 + t) * p.ld_dqkv + head * p.hd;
+      bf16* op = p.dqkv + (long long)(row0 + t) * p.ld_dqkv + head * p.hd + hf * 32;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q * 8 < p.hd) {
+      for (int q = 0; q < 4; ++q) {
+        if (hf * 32 + q * 8 < p.hd) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = dq[q * 8 + i];
@@ -515,20 +538,20 @@ __global__ void __launch_bounds__((4 * kDqGroups + kDqGroups) * 32, kDqGroups ==
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4 * NG) {
+  if (warp == kBwdRowWarps * NG) {
     tc_fence_after();
     tmem_dealloc(*tmem_slot, pow2_cols(NG * 256));
   }
 }
 
 // =============================================================================================== backward: dK, dV
-__global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups == 1 ? 2 : 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32, kDkvGroups == 1 ? 2 : 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                     const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
   constexpr int NG = kDkvGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) pdl_launch_dependents();
-  const bool is_ctrl = warp >= 4 * NG;
-  const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
+  const bool is_ctrl = warp >= kBwdRowWarps * NG;
+  const int g = is_ctrl ? warp - kBwdRowWarps * NG : warp / kBwdRowWarps;  // group of this warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem = smem0 + g * kDkvGroupBytes;
@@ -567,13 +590,13 @@ __global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups
       mbar_init(&q_free[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 128);
+    mbar_init(pds_ready, 32 * kBwdRowWarps);
     mbar_init(acc_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
   }
-  if (warp == 4 * NG) {
+  if (warp == kBwdRowWarps * NG) {
     tmem_alloc(tmem_slot, pow2_cols(NG * 256));  // per group (256 columns): Sᵀ 0-63, dPᵀ 64-127, dV 128-191, dK 192-255
     tmem_relinquish();
   }
@@ -635,38 +658,47 @@ __global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups
       }
     }
   } else {
-    const int r = threadIdx.x & 127;
+    const int r = threadIdx.x & 127, hf = (threadIdx.x >> 7) & 1;  // key row of the block, query-column half of every step
     const int kk = kstart + r;  // this thread's key
-    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, 0);
+    const uint32_t lane_addr = tmem_addr(tmem_base, (warp & 3) * 32, hf * 32);
     const long long stat0 = ((long long)b * p.nh + head) * p.T;
     for (int ii = 0; ii < n_q; ++ii) {
       const int q0 = kstart + ii * BK;
       {  // stage the 64 queries' lse / delta (double buffered; the barrier below orders reuse)
-        const int c = r & 63;
-        const int tq = q0 + c;
-        float* dst = (r < 64 ? s_lse : s_dl) + (ii & 1) * 64;
-        const float* src = r < 64 ? p.lse : p.delta;
-        dst[c] = tq < p.T ? src[stat0 + tq] : 0.f;
+        const int w = threadIdx.x & 255;
+        if (w < 128) {
+          const int c = w & 63;
+          const int tq = q0 + c;
+          float* dst = (w < 64 ? s_lse : s_dl) + (ii & 1) * 64;
+          const float* src = w < 64 ? p.lse : p.delta;
+          dst[c] = tq < p.T ? src[stat0 + tq] : 0.f;
+        }
       }
-      named_bar_sync(1 + g, 128);
-      const float* lse = s_lse + (ii & 1) * 64;
-      const float* dl = s_dl + (ii & 1) * 64;
+      named_bar_sync(1 + g, 32 * kBwdRowWarps);
+      const float4* lse4 = reinterpret_cast<const float4*>(s_lse + (ii & 1) * 64 + hf * 32);
+      const float4* dl4 = reinterpret_cast<const float4*>(s_dl + (ii & 1) * 64 + hf * 32);
       attn_wait(sdp_full, ii & 1);
       tc_fence_after();
-      float s[64], dp[64];
-      ld64(lane_addr, s);
-      ld64(lane_addr + 64, dp);
+      float s[32], dp[32];
+      ld32(lane_addr, s);
+      ld32(lane_addr + 64, dp);
       const bool edge = (q0 < kstart + BQ) || (q0 + BK > p.T) || (kstart + BQ > p.T);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const int tq = q0 + c;
-        float pr = fast_exp2(fmaf(s[c], p.scale_log2, -lse[c]));
-        if (edge && (kk > tq || tq >= p.T || kk >= p.T)) pr = 0.f;
-        s[c] = pr;
-        dp[c] = pr * (dp[c] - dl[c]) * p.scale;
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 l4 = lse4[c4], d4 = dl4[c4];  // 16 vector loads per step instead of 128 scalar broadcasts
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c4 * 4 + i;
+          const int tq = q0 + hf * 32 + c;
+          float pr = fast_exp2(fmaf(s[c], p.scale_log2, -ls[i]));
+          if (edge && (kk > tq || tq >= p.T || kk >= p.T)) pr = 0.f;
+          s[c] = pr;
+          dp[c] = pr * (dp[c] - ds[i]) * p.scale;
+        }
       }
-      store_row64(sPt, r, s);
-      store_row64(sdSt, r, dp);
+      store_row32(sPt, r, hf, s);
+      store_row32(sdSt, r, hf, dp);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_ready);
@@ -675,15 +707,15 @@ __global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups
       attn_wait(acc_full, 0);
       tc_fence_after();
     }
-    float acc[64];
+    float acc[32];
 #pragma unroll 1
     for (int which = 0; active && which < 2; ++which) {  // 0: dV -> v slot, 1: dK -> k slot
-      ld64(lane_addr + 128 + which * 64, acc);
+      ld32(lane_addr + 128 + which * 64, acc);
       if (kk < p.T) {
-        bf16* op = p.dqkv + (long long)(row0 + kk) * p.ld_dqkv + (long long)((which == 0 ? 2 : 1) * p.nh + head) * p.hd;
+        bf16* op = p.dqkv + (long long)(row0 + kk) * p.ld_dqkv + (long long)((which == 0 ? 2 : 1) * p.nh + head) * p.hd + hf * 32;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q * 8 < p.hd) {
+        for (int q = 0; q < 4; ++q) {
+          if (hf * 32 + q * 8 < p.hd) {
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = acc[q * 8 + i];
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__((4 * kDkvGroups + kDkvGroups) * 32, kDkvGroups
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4 * NG) {
+  if (warp == kBwdRowWarps * NG) {
     tc_fence_after();
     tmem_dealloc(*tmem_slot, pow2_cols(NG * 256));
   }
@@ -744,7 +776,7 @@ void check_shape(int B, int T, int nh, int hd) {
 constexpr int kFwdSmem = kFwdGroups * kFwdGroupBytes + 1024;
 constexpr int kDqSmem = kDqGroups * kDqGroupBytes + 1024;
 constexpr int kDkvSmem = kDkvGroups * kDkvGroupBytes + 1024;
-constexpr int kFwdThreads = 5 * kFwdGroups * 32, kDqThreads = 5 * kDqGroups * 32, kDkvThreads = 5 * kDkvGroups * 32;
+constexpr int kFwdThreads = 5 * kFwdGroups * 32, kDqThreads = (kBwdRowWarps + 1) * kDqGroups * 32, kDkvThreads = (kBwdRowWarps + 1) * kDkvGroups * 32;
 
 void* g_attn_trace = nullptr;
 int g_attn_occupancy[3] = {0, 0, 0};  // resident CTAs per SM reported for fwd / dq / dkv
