@@ -63,6 +63,28 @@ def parse_args(argv=None):
     p.add_argument("--overwrite_output_dir", action="store_true")
     p.add_argument("--save_model", action="store_true", help="the reference forces save_strategy='no'; opt in to a final save")
     p.add_argument("--device", default="auto")
+    # ---- the rest of the HF `TrainingArguments` / data-argument surface the reference script is usually driven with
+    # (run_glue.py:222-390 upstream hands these to transformers.Trainer; here they configure the loop below)
+    p.add_argument("--dataset_name", default=None, help="datasets hub / local dataset name (alternative to --task_name / --train_file)")
+    p.add_argument("--dataset_config_name", default=None)
+    p.add_argument("--max_predict_samples", type=int, default=None)
+    p.add_argument("--gradient_accumulation_steps", type=int, default=1)
+    p.add_argument("--lr_scheduler_type", default="linear", choices=["linear", "cosine", "constant", "constant_with_warmup"])
+    p.add_argument("--warmup_steps", type=int, default=0, help="overrides --warmup_ratio when > 0")
+    p.add_argument("--adam_beta1", type=float, default=0.9)
+    p.add_argument("--adam_beta2", type=float, default=0.999)
+    p.add_argument("--adam_epsilon", type=float, default=1e-8)
+    p.add_argument("--logging_steps", type=int, default=50)
+    p.add_argument("--evaluation_strategy", "--eval_strategy", dest="evaluation_strategy", default="no", choices=["no", "steps", "epoch"])
+    p.add_argument("--eval_steps", type=int, default=None)
+    p.add_argument("--save_strategy", default="no", help="accepted for CLI parity; the reference forces 'no' (run_glue.py:222)")
+    p.add_argument("--fp16", action="store_true", help="refused like the trainer (args_utils.py:56-57): use --bf16")
+    p.add_argument("--report_to", default="none")
+    p.add_argument("--run_name", default=None)
+    p.add_argument("--cache_dir", default=None)
+    p.add_argument("--use_fast_tokenizer", default=True, type=lambda s: str(s).lower() == "true")
+    p.add_argument("--overwrite_cache", action="store_true")
+    p.add_argument("--ignore_mismatched_sizes", action="store_true")
     return p.parse_args(argv)
 
 
@@ -98,7 +120,11 @@ def _load_raw(args):
     import datasets
 
     if args.task_name is not None and args.train_file is None:
-        return datasets.load_dataset("glue", args.task_name)
+        return datasets.load_dataset("glue", args.task_name, cache_dir=args.cache_dir)
+    if args.dataset_name is not None and args.train_file is None:
+        if os.path.isdir(args.dataset_name):
+            return datasets.load_from_disk(args.dataset_name)
+        return datasets.load_dataset(args.dataset_name, args.dataset_config_name, cache_dir=args.cache_dir)
     files = {k: v for k, v in (("train", args.train_file), ("validation", args.validation_file), ("test", args.test_file)) if v}
     ext = "csv" if next(iter(files.values())).endswith(".csv") else "json"
     return datasets.load_dataset(ext, data_files=files)
@@ -161,6 +187,8 @@ def _load_model(path: str, num_labels: int, pad_id: int, problem_type: Optional[
 
 def main(argv=None):
     args = parse_args(argv)
+    if args.fp16:
+        raise ValueError("fp16 is not supported (the pre-training weights are bf16); use --bf16")
     random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed)
     if os.path.isdir(args.output_dir) and os.listdir(args.output_dir) and args.do_train and not args.overwrite_output_dir:
         raise ValueError(f"Output directory ({args.output_dir}) already exists and is not empty. Use --overwrite_output_dir to overcome.")
@@ -169,7 +197,7 @@ def main(argv=None):
 
     from transformers import AutoTokenizer
 
-    tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name or args.model_name_or_path)
+    tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name or args.model_name_or_path, use_fast=args.use_fast_tokenizer, cache_dir=args.cache_dir)
     raw = _load_raw(args)
     task = args.task_name
     is_regression = task == "stsb" or (task is None and "float" in str(raw["train"].features["label"].dtype))
@@ -198,39 +226,11 @@ def main(argv=None):
             j = idx[i: i + bs]
             yield x[j].to(device), (y[j].to(device) if y is not None else None)
 
-    results: Dict[str, float] = {}
-    if args.do_train:
-        x, y = data["train"]
-        if args.max_train_samples:
-            x, y = x[: args.max_train_samples], y[: args.max_train_samples]
-        steps_per_epoch = math.ceil(len(x) / args.per_device_train_batch_size)
-        total = args.max_steps if args.max_steps > 0 else int(steps_per_epoch * args.num_train_epochs)
-        opt = torch.optim.AdamW(model.parameters(), lr=args.learning_rate, weight_decay=args.weight_decay)
-        warm = int(args.warmup_ratio * total)
-        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: s / max(1, warm) if s < warm else max(0.0, (total - s) / max(1, total - warm)))
-        model.train()
-        step, done = 0, False
-        while not done:
-            for xb, yb in batches(x, y, args.per_device_train_batch_size, True):
-                with torch.autocast(device.type, dtype=torch.bfloat16, enabled=args.bf16):
-                    loss = model(input_ids=xb, labels=yb).loss
-                loss.backward()
-                torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)
-                opt.step(); sched.step(); opt.zero_grad(set_to_none=True)
-                step += 1
-                if step % 50 == 0 or step == total:
-                    logger.info(f"step {step}/{total} loss {float(loss):.4f} lr {sched.get_last_lr()[0]:.2e}")
-                if step >= total:
-                    done = True
-                    break
-        results["train_loss"] = float(loss)
-        if args.save_model:
-            model.save_pretrained(args.output_dir)
-
     def evaluate(split):
         x, y = data[split]
-        if args.max_eval_samples:
-            x, y = x[: args.max_eval_samples], (y[: args.max_eval_samples] if y is not None else None)
+        cap = args.max_predict_samples if split == "test" else args.max_eval_samples
+        if cap:
+            x, y = x[:cap], (y[:cap] if y is not None else None)
         model.eval()
         outs = []
         with torch.no_grad():
@@ -240,6 +240,61 @@ def main(argv=None):
         logits = torch.cat(outs)
         preds = logits.squeeze(-1).numpy() if is_regression else logits.argmax(-1).numpy()
         return preds, (y.numpy() if y is not None else None)
+
+    results: Dict[str, float] = {}
+    if args.do_train:
+        x, y = data["train"]
+        if args.max_train_samples:
+            x, y = x[: args.max_train_samples], y[: args.max_train_samples]
+        ga = max(1, args.gradient_accumulation_steps)
+        micro_per_epoch = math.ceil(len(x) / args.per_device_train_batch_size)
+        steps_per_epoch = max(1, micro_per_epoch // ga)
+        total = args.max_steps if args.max_steps > 0 else int(steps_per_epoch * args.num_train_epochs)
+        opt = torch.optim.AdamW(model.parameters(), lr=args.learning_rate, weight_decay=args.weight_decay,
+                                betas=(args.adam_beta1, args.adam_beta2), eps=args.adam_epsilon)
+        warm = args.warmup_steps if args.warmup_steps > 0 else int(args.warmup_ratio * total)
+
+        def lr_lambda(st):
+            if st < warm and args.lr_scheduler_type != "constant":
+                return st / max(1, warm)
+            if args.lr_scheduler_type in ("constant", "constant_with_warmup"):
+                return 1.0
+            frac = (st - warm) / max(1, total - warm)
+            if args.lr_scheduler_type == "cosine":
+                return max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, frac))))
+            return max(0.0, 1.0 - frac)
+
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda)
+        eval_every = None
+        if args.evaluation_strategy == "steps":
+            eval_every = args.eval_steps or args.logging_steps
+        elif args.evaluation_strategy == "epoch":
+            eval_every = steps_per_epoch
+        model.train()
+        step, micro, done = 0, 0, False
+        while not done:
+            for xb, yb in batches(x, y, args.per_device_train_batch_size, True):
+                with torch.autocast(device.type, dtype=torch.bfloat16, enabled=args.bf16):
+                    loss = model(input_ids=xb, labels=yb).loss
+                (loss / ga).backward()
+                micro += 1
+                if micro % ga:
+                    continue
+                torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)
+                opt.step(); sched.step(); opt.zero_grad(set_to_none=True)
+                step += 1
+                if step % max(1, args.logging_steps) == 0 or step == total:
+                    logger.info(f"step {step}/{total} loss {float(loss):.4f} lr {sched.get_last_lr()[0]:.2e}")
+                if eval_every and step % eval_every == 0 and "validation" in data and step < total:
+                    preds, labels = evaluate("validation")
+                    logger.info(f"step {step}: {glue_metrics(task, preds, labels)}")
+                    model.train()
+                if step >= total:
+                    done = True
+                    break
+        results["train_loss"] = float(loss)
+        if args.save_model:
+            model.save_pretrained(args.output_dir)
 
     if args.do_eval:
         splits = ["validation_matched", "validation_mismatched"] if task == "mnli" else ["validation"]
