@@ -62,7 +62,7 @@ def _default_dtype() -> str:
 # flags that only exist in this engine; allowed next to --training_config
 ENGINE_FLAGS = (
     "--device", "--backend", "--comm", "--engine", "--lora_dropout", "--cuda_graphs", "--frozen_dtype",
-    "--init_lora_a", "--synthetic_data", "--log_every", "--parity_quirks", "--attention",
+    "--init_lora_a", "--synthetic_data", "--log_every", "--parity_quirks", "--attention", "--deterministic",
 )
 
 
@@ -139,6 +139,8 @@ def build_parser() -> argparse.ArgumentParser:
                    help="fused: whole-layer sm_100a executor (+CUDA graphs); module: nn.Module path")
     p.add_argument("--lora_dropout", type=float, default=0.1, help="hard-coded to 0.1 upstream (torchrun_main.py:546)")
     _add_bool(p, "--cuda_graphs", True)
+    _add_bool(p, "--deterministic", False,
+              help="fixed summation order for the weight-gradient GEMMs (no split-K atomics; slower) on top of the always-deterministic embedding backward")
     p.add_argument("--attention", type=str, default="auto", choices=["auto", "native", "sdpa"],
                    help="native: tcgen05 flash-attention kernels of this repo (head_dim <= 64); sdpa: torch SDPA (cuDNN)")
     p.add_argument("--frozen_dtype", type=str, default=None, choices=[None, "bf16", "fp8", "fp8_full", "mxfp8", "nvfp4"],

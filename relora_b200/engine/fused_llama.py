@@ -78,7 +78,8 @@ class FusedLlamaStepper:
     def __init__(self, model: ReLoRaModel, info: DistInfo, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, clip_grad_norm: float = 1.0, grad_accumulation: int = 1, zero: bool = False,
                  transport: str = "nccl", native=None, symm_factory=None, cuda_graphs: bool = True, ce_chunk: int = 4096,
-                 overlap_wgrad: bool = True, attention: str = "auto", fp8: bool = False, fp8_backward: bool = False):
+                 overlap_wgrad: bool = True, attention: str = "auto", fp8: bool = False, fp8_backward: bool = False,
+                 deterministic: bool = False):
         ok, why = supports(model)
         if not ok:
             raise RuntimeError(why)
@@ -278,6 +279,10 @@ class FusedLlamaStepper:
         # break-even near 4096; with fp8 input-gradient GEMMs (twice the rate) at 2048.
         self.dx_split_k = int(os.environ.get("RELORA_B200_DX_SPLIT_K", "0")) or (2048 if self.fp8_bwd else 4096)
         self._wg_done: Dict[str, torch.cuda.Event] = {}
+        # --deterministic: the stacked dA / dB weight-gradient GEMMs run without split-K (one CTA owns an output tile for the whole token
+        # reduction: fixed summation order instead of fp32 atomics from several CTAs).  Remaining order-dependent reductions are the
+        # [h]-sized norm-weight gradients (block partials combined with vector atomics).
+        self.wgrad_split_k = 1 if (deterministic or os.environ.get("RELORA_B200_DETERMINISTIC", "0") == "1") else 0
         # embedding backward without atomics (default); RELORA_B200_ATOMIC_EMBEDDING=1 selects the atomicAdd scatter
         self.deterministic_embedding = os.environ.get("RELORA_B200_ATOMIC_EMBEDDING", "0") != "1"
 
@@ -485,10 +490,10 @@ class FusedLlamaStepper:
         shared_x = (not drop) or xd.shape[1] != G * K
 
         def wgrads():  # fp32, accumulated across micro-batches, split-K over tokens
-            g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+            g(du, xd, gA, M=G * r, N=K, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=self.wgrad_split_k,
               m_per_group=r if G > 1 else 0, b1_mn_ofs_per_mgroup=0 if shared_x else K)
             # fp8 path: the saved u is u / (s_x·s_w); the product scale is multiplied back here
-            g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=0,
+            g(dy, u, gB, M=G * Ng, N=r, K1=M, a1_mn=True, b1_mn=True, accumulate=True, split_k=self.wgrad_split_k,
               m_per_group=Ng if G > 1 else 0, b1_mn_ofs_per_mgroup=r if G > 1 else 0,
               alpha_dev=self.alpha_main[site[0], site[1]:site[1] + 1] if (self.fp8 and site is not None) else None)
 

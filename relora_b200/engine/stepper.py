@@ -195,7 +195,8 @@ def make_stepper(model, info: DistInfo, args, *, native=None, symm_factory=None)
             return FusedLlamaStepper(model, info, cuda_graphs=getattr(args, "cuda_graphs", True),
                                      attention=getattr(args, "attention", "auto"),
                                      fp8=getattr(args, "frozen_dtype", None) in ("fp8", "fp8_full"),
-                                     fp8_backward=getattr(args, "frozen_dtype", None) == "fp8_full", **kw)
+                                     fp8_backward=getattr(args, "frozen_dtype", None) == "fp8_full",
+                                     deterministic=bool(getattr(args, "deterministic", False)), **kw)
         if engine == "fused":
             raise RuntimeError(f"--engine fused requested but not applicable: {why}")
     if info.device.type != "cuda":

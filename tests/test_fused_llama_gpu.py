@@ -223,3 +223,25 @@ def test_cli_quantized_frozen_weights_train_on_packed_storage(tmp_path, quant):
     sd = torch.load(os.path.join(d, "model_8", "pytorch_model.bin"), weights_only=True)
     w = sd["model.layers.0.self_attn.q_proj.weight"]
     assert w.shape == (256, 256) and bool(torch.isfinite(w.float()).all())
+
+
+def test_deterministic_mode_reproduces_lora_and_embedding_gradients_bit_for_bit():
+    """`--deterministic`: weight-gradient GEMMs without split-K atomics + the sorted embedding backward -> two runs of the same
+    micro-batch give bit-identical LoRA / embedding / LM-head gradients (the default split-K path may differ in the last bits)."""
+    from relora_b200.engine.fused_llama import FusedLlamaStepper
+    from relora_b200.ops import fused
+
+    dev = torch.device("cuda", 0)
+    ids = torch.randint(0, 4095, (3, 128), device=dev)
+    grads = []
+    for _ in range(2):
+        w = _build(0.1, seed=3)
+        fs = FusedLlamaStepper(w, _info(), lr=1e-3, grad_accumulation=1, cuda_graphs=False, deterministic=True)
+        fused.seed_state.set(dev, 99)
+        fs.micro_step(ids)
+        torch.cuda.synchronize()
+        grads.append({n: fs.store.view_like(fs.store.grads, p).clone() for n, p in zip(fs.trainable_names, fs.trainable_params)})
+    for n in grads[0]:
+        if "layernorm" in n or n.endswith("norm.weight"):
+            continue  # [h]-sized norm gradients are combined with vector atomics (documented)
+        assert torch.equal(grads[0][n], grads[1][n]), n
