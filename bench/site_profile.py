@@ -118,6 +118,11 @@ def main():
                 if dn:
                     by = tensor_bytes(args, kw)
                     tag, fl = name, 0.0
+                    if name in ("attention_fwd", "attention_bwd"):
+                        Bq, Tq, nhq, hdq = (int(v) for v in (args[3:7] if name == "attention_fwd" else args[6:10]))
+                        fwd = 2.0 * Bq * nhq * Tq * Tq * hdq  # causal: half of the 4·B·nh·T²·hd of S = QKᵀ and O = PV
+                        fl = fwd if name == "attention_fwd" else 2.5 * fwd  # backward: 5 products instead of 2
+                        tag = "%s B%d T%d nh%d hd%d" % (name, Bq, Tq, nhq, hdq)
                     if name == "lora_dx":
                         dy, w, du, aa, out = args[:5]
                         base = args[8] if len(args) > 8 else kw.get("base")
