@@ -27,7 +27,9 @@ for name, B, T, nh, hd in (("250m", 24, 512, 16, 48), ("1b", 16, 512, 32, 64), (
     dqkv = torch.empty_like(qkv)
     sc = 1.0 / math.sqrt(hd)
     t_f = timeit(lambda: C.attention_fwd(qkv, out, lse, B, T, nh, hd, sc))
-    t_b = timeit(lambda: C.attention_bwd(qkv, out, dout, lse, delta, dqkv, B, T, nh, hd, sc))
+    t_b_recompute = timeit(lambda: C.attention_bwd(qkv, out, dout, lse, delta, dqkv, B, T, nh, hd, sc))
+    ws = torch.empty(C.attention_ds_workspace_elems(B, T, nh), device="cuda", dtype=torch.bfloat16)
+    t_b = timeit(lambda: C.attention_bwd(qkv, out, dout, lse, delta, dqkv, B, T, nh, hd, sc, ws))  # default: dS stored, dQ = dS·K
     v5 = qkv.view(B, T, 3, nh, hd)
     q, k, v = (v5[:, :, i].transpose(1, 2).detach().requires_grad_() for i in range(3))
     t_sf = timeit(lambda: Fn.scaled_dot_product_attention(q, k, v, is_causal=True))
@@ -35,7 +37,7 @@ for name, B, T, nh, hd in (("250m", 24, 512, 16, 48), ("1b", 16, 512, 32, 64), (
     g = dout.view(B, T, nh, hd).transpose(1, 2)
     t_sb = timeit(lambda: torch.autograd.grad(o, (q, k, v), g, retain_graph=True))
     fl = 4.0 * B * nh * T * T * hd / 2
-    rec = {"shape": name, "B": B, "T": T, "nh": nh, "hd": hd, "ours_fwd_us": t_f, "sdpa_fwd_us": t_sf, "ours_bwd_us": t_b, "sdpa_bwd_us": t_sb,
+    rec = {"shape": name, "B": B, "T": T, "nh": nh, "hd": hd, "ours_fwd_us": t_f, "sdpa_fwd_us": t_sf, "ours_bwd_us": t_b, "ours_bwd_recompute_us": t_b_recompute, "sdpa_bwd_us": t_sb,
            "ours_fwd_tflops": fl / t_f / 1e6, "ours_bwd_tflops": 2.5 * fl / t_b / 1e6}
     rows.append(rec); print(json.dumps({k: (round(x, 1) if isinstance(x, float) else x) for k, x in rec.items()}), flush=True)
 print("resident CTAs per SM (fwd, dq, dkv):", [C.attention_occupancy(i) for i in range(3)])

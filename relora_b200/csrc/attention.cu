@@ -382,6 +382,7 @@ struct BwdArgs {
   long long ld_dqkv;
   int B, T, nh, hd;
   float scale, scale_log2;
+  int store_ds;  // dK/dV kernel also writes its dSᵀ tiles to global memory (consumed by attn_bwd_dq2_kernel)
 };
 
 // =============================================================================================== backward: dQ
@@ -546,7 +547,8 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDqGroups + kDqGroups) * 32, k
 
 // =============================================================================================== backward: dK, dV
 __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32, kDkvGroups == 1 ? 2 : 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv,
-                                                                    const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
+                                                                    const __grid_constant__ CUtensorMap map_do,
+                                                                    const __grid_constant__ CUtensorMap map_ds, const BwdArgs p) {
   constexpr int NG = kDkvGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) pdl_launch_dependents();
@@ -595,6 +597,7 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
     fence_barrier_init();
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
+    if (p.store_ds) tma_prefetch_desc(&map_ds);
   }
   if (warp == kBwdRowWarps * NG) {
     tmem_alloc(tmem_slot, pow2_cols(NG * 256));  // per group (256 columns): Sᵀ 0-63, dPᵀ 64-127, dV 128-191, dK 192-255
@@ -644,12 +647,20 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tmem_base + 192, desc_k(sdSt, k), desc_mn(sQ + st * kTile64, k), idesc_kmn, (ii | k) != 0);
         umma_commit(&q_free[st]);
+        if (p.store_ds) {
+          // dSᵀ tile [128 keys x 64 queries] -> global [b*nh+head][key][query]: the dQ kernel then is a plain TMA -> MMA pipeline
+          // (dQ = dS·K) instead of recomputing S and dP (the row threads fenced their writes before arriving on pds_ready)
+          tma_store_3d(&map_ds, sdSt, kstart + ii * BK, kstart, b * p.nh + head);
+          tma_store_commit();
+        }
         if (ii + 1 < n_q) {
           attn_wait(&q_full[st ^ 1], ((ii + 1) >> 1) & 1);
           tc_fence_after();
+          if (p.store_ds) tma_store_wait_read<0>();  // the next step's row threads overwrite the tile once sdp_full fires
           issue_sdp(st ^ 1);
         } else {
           umma_commit(acc_full);
+          if (p.store_ds) tma_store_wait<0>();
         }
         if (ii + 2 < n_q) {
           attn_wait(&q_free[st], (ii >> 1) & 1);
@@ -730,6 +741,112 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
   if (warp == kBwdRowWarps * NG) {
     tc_fence_after();
     tmem_dealloc(*tmem_slot, pow2_cols(NG * 256));
+  }
+}
+
+// =============================================================================================== backward: dQ from stored dS
+// dQ[q, :] = Σ_k dS[q, k] · K[k, :] with dSᵀ tiles written by the dK/dV kernel: no scores, no exponentials, no row-thread work inside
+// the loop -- a two-stage TMA -> tcgen05 pipeline per (128 queries, head, batch).  A = dSᵀ tile [128 keys x 128 queries] read MN-major
+// (M = queries), B = K tile [128 keys x head_dim] read MN-major (N = head_dim), K = 128 keys per stage.
+constexpr int kDq2StageBytes = 2 * kTile128 + 2 * kTile64;   // dSᵀ (two 64-query chunks) + K (two 64-key tiles)
+constexpr int kDq2Smem = 2 * kDq2StageBytes + 1024 + 1024;
+__global__ void __launch_bounds__(160, 2) attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_ds,
+                                                              const BwdArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_ctrl = warp >= 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kDq2StageBytes);
+  uint64_t* full = bars;       // [2]
+  uint64_t* free_ = bars + 2;  // [2]
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int nqb = (p.T + BQ - 1) / BQ;
+  const long long per = (long long)p.B * p.nh;
+  const long long item = blockIdx.x;
+  const int qb = nqb - 1 - int(item / per);  // heaviest (latest) query blocks first
+  const int head = int((item % per) % p.nh), b = int((item % per) / p.nh);
+  const int t0 = qb * BQ;
+  const int row0 = b * p.T;
+  const int n_kb = qb + 1;  // causal: key blocks 0 .. qb
+
+  if (is_ctrl && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&free_[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_ds);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (is_ctrl) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      auto load = [&](int kb, int st) {
+        uint8_t* sA = smem + st * kDq2StageBytes;
+        uint8_t* sB = sA + 2 * kTile128;
+        mbar_arrive_expect_tx(&full[st], kDq2StageBytes);
+        tma_load_3d(&map_ds, &full[st], sA, t0, kb * BQ, b * p.nh + head);
+        tma_load_3d(&map_ds, &full[st], sA + kTile128, t0 + 64, kb * BQ, b * p.nh + head);
+        tma_load_3d(&map_qkv, &full[st], sB, 0, p.nh + head, row0 + kb * BQ);
+        tma_load_3d(&map_qkv, &full[st], sB + kTile64, 0, p.nh + head, row0 + kb * BQ + 64);
+      };
+      load(0, 0);
+      if (n_kb > 1) load(1, 1);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int st = kb & 1;
+        attn_wait(&full[st], (kb >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + st * kDq2StageBytes), sB = sA + 2 * kTile128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // 16 keys per instruction; A: query chunks of 64 are 16 KB apart, 8-key groups 1 KB apart
+          umma_f16_ss(tmem_base, make_desc_sw128(sA + k * 2048, kTile128, 1024), make_desc_sw128(sB + k * 2048, 8192, 1024), idesc,
+                      (kb | k) != 0);
+        umma_commit(&free_[st]);
+        if (kb + 2 < n_kb) {
+          attn_wait(&free_[st], (kb >> 1) & 1);
+          load(kb + 2, st);
+        }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int r = threadIdx.x & 127;
+    const int t = t0 + r;
+    attn_wait(done, 0);
+    tc_fence_after();
+    float dq[64];
+    ld64(tmem_addr(tmem_base, (warp & 3) * 32, 0), dq);
+    if (t < p.T) {
+      bf16* op = p.dqkv + (long long)(row0 + t) * p.ld_dqkv + head * p.hd;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q * 8 < p.hd) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = dq[q * 8 + i];
+          *reinterpret_cast<uint4*>(op + q * 8) = pack8(f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -854,10 +971,33 @@ void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream) {
   p.B = d.B; p.T = d.T; p.nh = d.nh; p.hd = d.hd;
   p.scale = d.scale; p.scale_log2 = d.scale * 1.4426950408889634f;
   const long long items = (long long)((d.T + BQ - 1) / BQ) * d.nh * d.B;
-  launch_k(attn_bwd_dkv_kernel, dim3((unsigned)((items + kDkvGroups - 1) / kDkvGroups)), kDkvThreads, kDkvSmem, stream, map_qkv, map_do, p);
+  p.store_ds = d.ds_workspace != nullptr ? 1 : 0;
+  CUtensorMap map_ds = map_do;
+  if (p.store_ds) {
+    // dSᵀ workspace [B*nh][Tp keys][Tp queries] bf16, Tp = T rounded up to 64 (16-byte pitch for any T); tiles of 64 queries x 128 keys
+    const long long Tp = attention_ds_pitch(d.T);
+    map_ds = make_map_3d_bf16(d.ds_workspace, d.T, d.T, (long long)d.B * d.nh, Tp, Tp * Tp, 64, 128, 1);
+  }
+  launch_k(attn_bwd_dkv_kernel, dim3((unsigned)((items + kDkvGroups - 1) / kDkvGroups)), kDkvThreads, kDkvSmem, stream, map_qkv, map_do, map_ds, p);
   RB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-  launch_k(attn_bwd_dq_kernel, dim3((unsigned)((items + kDqGroups - 1) / kDqGroups)), kDqThreads, kDqSmem, stream, map_qkv, map_do, p);
-  RB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+  if (p.store_ds) {
+    static bool cfg2 = false;
+    if (!cfg2) {
+      check(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq2Smem), "attr(attn_bwd_dq2)");
+      cfg2 = true;
+    }
+    launch_k(attn_bwd_dq2_kernel, dim3((unsigned)items), 160, kDq2Smem, stream, map_qkv, map_ds, p);
+    RB_CHECK_LAUNCH("attn_bwd_dq2_kernel");
+  } else {
+    launch_k(attn_bwd_dq_kernel, dim3((unsigned)((items + kDqGroups - 1) / kDqGroups)), kDqThreads, kDqSmem, stream, map_qkv, map_do, p);
+    RB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+  }
+}
+
+long long attention_ds_pitch(int T) { return ((long long)T + 63) / 64 * 64; }
+long long attention_ds_workspace_elems(int B, int T, int nh) {
+  const long long Tp = attention_ds_pitch(T);
+  return (long long)B * nh * Tp * Tp;
 }
 
 }  // namespace rb

@@ -35,8 +35,13 @@ struct AttnBwdDesc {
   long long ld_dqkv = 0;
   int B = 0, T = 0, nh = 0, hd = 0;
   float scale = 1.0f;
+  // optional bf16 workspace of attention_ds_workspace_elems(B, T, nh) elements: the dK/dV kernel stores its dSᵀ tiles there and dQ
+  // becomes a plain TMA -> MMA kernel (dQ = dS·K) instead of recomputing S and dP; nullptr = the recomputing dQ kernel
+  void* ds_workspace = nullptr;
 };
 void attention_bwd(const AttnBwdDesc& d, cudaStream_t stream);
+long long attention_ds_pitch(int T);
+long long attention_ds_workspace_elems(int B, int T, int nh);
 
 // Diagnostics: the heaviest forward CTA writes clock64 stamps (8 x 64 int64) into `buf`; nullptr = off.
 void attention_set_trace(void* buf);

@@ -273,7 +273,7 @@ void attention_fwd(const Tensor& qkv, Tensor& out, Tensor& lse, int64_t B, int64
   rb::attention_fwd(d, cur_stream());
 }
 void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, const Tensor& lse, Tensor& delta, Tensor& dqkv, int64_t B,
-                   int64_t T, int64_t nh, int64_t hd, double scale) {
+                   int64_t T, int64_t nh, int64_t hd, double scale, const OptTensor& ds_workspace) {
   chk_bf16(qkv, "qkv"); chk_bf16(out, "out"); chk_bf16(dout, "dout"); chk_bf16(dqkv, "dqkv");
   chk_2d_rowmajor(qkv, "qkv"); chk_2d_rowmajor(out, "out"); chk_2d_rowmajor(dout, "dout"); chk_2d_rowmajor(dqkv, "dqkv");
   TORCH_CHECK(qkv.size(0) == B * T && qkv.size(1) == 3 * nh * hd && dqkv.size(0) == B * T && dqkv.size(1) == 3 * nh * hd, "qkv / dqkv must be [B*T, 3*nh*hd]");
@@ -285,6 +285,12 @@ void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, con
   d.dout = dout.data_ptr(); d.ld_dout = dout.stride(0); d.lse = lse.data_ptr<float>(); d.delta = delta.data_ptr<float>();
   d.dqkv = dqkv.data_ptr(); d.ld_dqkv = dqkv.stride(0);
   d.B = (int)B; d.T = (int)T; d.nh = (int)nh; d.hd = (int)hd; d.scale = (float)scale;
+  if (ds_workspace.has_value()) {
+    chk_bf16(*ds_workspace, "ds_workspace");
+    TORCH_CHECK(ds_workspace->is_contiguous() && ds_workspace->numel() >= rb::attention_ds_workspace_elems((int)B, (int)T, (int)nh),
+                "ds_workspace too small (attention_ds_workspace_elems)");
+    d.ds_workspace = ds_workspace->data_ptr();
+  }
   c10::cuda::CUDAGuard guard(qkv.device());
   rb::attention_bwd(d, cur_stream());
 }
@@ -628,7 +634,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 8 * 64, "trace buffer: int64 CUDA tensor of >= 512 elements");
     rb::attention_set_trace(t->data_ptr());
   });
-  m.def("attention_bwd", &attention_bwd);
+  m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("delta"), py::arg("dqkv"),
+        py::arg("B"), py::arg("T"), py::arg("nh"), py::arg("hd"), py::arg("scale"), py::arg("ds_workspace") = py::none());
+  m.def("attention_ds_workspace_elems", &rb::attention_ds_workspace_elems);
   m.def("lora_dx", &lora_dx, py::arg("dy"), py::arg("w"), py::arg("du"), py::arg("a"), py::arg("out"), py::arg("seed"), py::arg("keys"),
         py::arg("p"), py::arg("base") = py::none());
   m.def("rope_inplace", &rope_inplace);

@@ -345,6 +345,9 @@ class FusedLlamaStepper:
             self.attn_o = e(L, M, h)
             self.lse = torch.empty(L, B, self.nh, T, dtype=torch.float32, device=dev)
             self.delta = torch.empty(B, self.nh, T, dtype=torch.float32, device=dev)
+            # dSᵀ workspace of the backward: the dK/dV kernel stores its tiles, dQ = dS·K runs as a plain TMA -> MMA kernel
+            self.ds_ws = (e(self.C.attention_ds_workspace_elems(B, T, self.nh))
+                          if os.environ.get("RELORA_B200_ATTN_DS", "1") != "0" else None)
         self.parts = e(M, max(3 * h, f))
         ldv = (self.V + 7) // 8 * 8
         self.logits = torch.zeros(min(self.ce_chunk, M), ldv, dtype=BF, device=dev)
@@ -568,7 +571,7 @@ class FusedLlamaStepper:
             if self.native_attn:
                 self._join("qkv")  # the previous layer's qkv weight gradients read dqkv / du_qkv
                 C.attention_bwd(self.qkv[l], self.attn_o[l], self.dattn, self.lse[l], self.delta, self.dqkv, B, T, nh, hd,
-                                1.0 / math.sqrt(hd))
+                                1.0 / math.sqrt(hd), self.ds_ws)
                 C.rope_inplace(self.dqkv, T, 2 * nh, hd, hd, self.cos, self.sin, True, 0)  # back through the rotation of q, k
                 dq = None
             else:

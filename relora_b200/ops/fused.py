@@ -6,6 +6,7 @@ when these are used.  Numerics oracles live in :mod:`.reference`.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -383,7 +384,10 @@ class _CausalAttentionFn(torch.autograd.Function):
             do = do.contiguous()
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device)
-        C.attention_bwd(qkv, out, do, lse, delta, dqkv, B, T, nh, hd, scale)
+        ds_ws = None
+        if os.environ.get("RELORA_B200_ATTN_DS", "1") != "0":
+            ds_ws = torch.empty(C.attention_ds_workspace_elems(B, T, nh), dtype=_BF16, device=qkv.device)
+        C.attention_bwd(qkv, out, do, lse, delta, dqkv, B, T, nh, hd, scale, ds_ws)
         d5 = dqkv.view(B, T, 3, nh, hd)
         return d5[:, :, 0].transpose(1, 2), d5[:, :, 1].transpose(1, 2), d5[:, :, 2].transpose(1, 2), None
 

@@ -574,12 +574,15 @@ def test_attention_fwd_bwd(C, B, T, nh, hd):
     dout = _rand(B * T, h, scale=0.5)
     want.backward(dout.view(B, T, nh, hd).transpose(1, 2).float())
     delta = torch.empty(B, nh, T, device="cuda", dtype=torch.float32)
-    dqkv = torch.zeros(B * T, 3 * h, device="cuda", dtype=BF)
-    C.attention_bwd(qkv, out, dout, lse, delta, dqkv, B, T, nh, hd, scale)
-    d5 = dqkv.view(B, T, 3, nh, hd)
-    for i, (name, ref_t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
-        e = _relerr(d5[:, :, i].transpose(1, 2), ref_t.grad)
-        assert e < 2e-2, (name, e)
+    # both backward forms: dQ recomputing S / dP, and dQ = dS·K from the dSᵀ tiles the dK/dV kernel stores (the default)
+    for use_ws in (False, True):
+        dqkv = torch.zeros(B * T, 3 * h, device="cuda", dtype=BF)
+        ws = torch.full((C.attention_ds_workspace_elems(B, T, nh),), float("nan"), device="cuda", dtype=BF) if use_ws else None
+        C.attention_bwd(qkv, out, dout, lse, delta, dqkv, B, T, nh, hd, scale, ws)
+        d5 = dqkv.view(B, T, 3, nh, hd)
+        for i, (name, ref_t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
+            e = _relerr(d5[:, :, i].transpose(1, 2), ref_t.grad)
+            assert e < 2e-2, (name, use_ws, e)
 
 
 # ----------------------------------------------------------------------------------------- fp8 frozen-weight path
