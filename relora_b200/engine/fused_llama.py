@@ -347,7 +347,7 @@ class FusedLlamaStepper:
             self.delta = torch.empty(B, self.nh, T, dtype=torch.float32, device=dev)
             # dSᵀ workspace of the backward: the dK/dV kernel stores its tiles, dQ = dS·K runs as a plain TMA -> MMA kernel
             self.ds_ws = (e(self.C.attention_ds_workspace_elems(B, T, self.nh))
-                          if os.environ.get("RELORA_B200_ATTN_DS", "0") != "0" else None)
+                          if os.environ.get("RELORA_B200_ATTN_DS", "1") != "0" else None)
         self.parts = e(M, max(3 * h, f))
         ldv = (self.V + 7) // 8 * 8
         self.logits = torch.zeros(min(self.ce_chunk, M), ldv, dtype=BF, device=dev)

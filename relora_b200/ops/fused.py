@@ -385,7 +385,7 @@ class _CausalAttentionFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device)
         ds_ws = None
-        if os.environ.get("RELORA_B200_ATTN_DS", "0") != "0":
+        if os.environ.get("RELORA_B200_ATTN_DS", "1") != "0":
             ds_ws = torch.empty(C.attention_ds_workspace_elems(B, T, nh), dtype=_BF16, device=qkv.device)
         C.attention_bwd(qkv, out, do, lse, delta, dqkv, B, T, nh, hd, scale, ds_ws)
         d5 = dqkv.view(B, T, 3, nh, hd)
