@@ -79,7 +79,10 @@ class SymmComm:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.C = native.require()
         if use_multicast is None:
-            use_multicast = os.environ.get("RELORA_B200_MULTICAST", "1") == "1"
+            # NVLS (multimem.ld_reduce / multimem.st through the switch) wins from 4 ranks up; between two GPUs plain peer loads / stores are
+            # faster (measured, profiles/multigpu/allreduce_n2_round2.json: fused update 550 vs 738 us, all-reduce 522 vs 330 GB/s at 64 MB)
+            env = os.environ.get("RELORA_B200_MULTICAST")
+            use_multicast = (env == "1") if env is not None else self.world > 2
         self.use_multicast = use_multicast
         self.max_blocks = max_blocks
         self.epoch = 0
