@@ -13,12 +13,12 @@ C = F._C()
 x = torch.randn(a.M, a.K, device="cuda").bfloat16(); W = (torch.randn(a.N, a.K, device="cuda") * 0.02).bfloat16()
 out = torch.empty(a.M, a.N, device="cuda", dtype=torch.bfloat16)
 for _ in range(3): F.gemm(x, W, out, block_n=a.bn, pair=a.pair)
-tr = torch.zeros(12 * 512, dtype=torch.int64, device="cuda")
+tr = torch.zeros(16 * 512, dtype=torch.int64, device="cuda")
 C.gemm_set_trace(tr)
 F.gemm(x, W, out, block_n=a.bn, pair=a.pair)
 torch.cuda.synchronize()
 C.gemm_set_trace(None)
-t = tr.view(12, 512).cpu()
+t = tr.view(16, 512).cpu()
 t0 = int(t[0, 0])
 names = ["load_issue", "mma_full", "acc_free", "tile_commit", "epi_start", "epi_end"]
 kb = (a.K + 63) // 64

@@ -612,7 +612,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_pair_clusters", &rb::gemm_pair_clusters);
   m.def("gemm_set_trace", [](const OptTensor& t) {
     if (!t.has_value()) { rb::gemm_set_trace(nullptr); return; }
-    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 12 * 512, "trace buffer: int64 CUDA tensor of >= 6144 elements");
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 16 * 512, "trace buffer: int64 CUDA tensor of >= 8192 elements");
     rb::gemm_set_trace(t->data_ptr());
   });
   m.def("rmsnorm_fwd", &rmsnorm_fwd, py::arg("x"), py::arg("w"), py::arg("y"), py::arg("rstd"), py::arg("eps"), py::arg("xd"), py::arg("seed"),

@@ -148,6 +148,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  if (p.trace != nullptr && threadIdx.x == 0) {  // rows 12-15: CTA 0 entry / setup / exit clocks; grid-wide first entry / last exit (ns)
+    if (blockIdx.x == 0) { p.trace[12 * 512 + 0] = clock64(); p.trace[13 * 512 + 0] = (long long)global_timer_ns(); }
+    atomicMin(reinterpret_cast<unsigned long long*>(p.trace + 14 * 512), global_timer_ns());
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a1);
@@ -186,6 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   pdl_wait();  // everything above is CTA-local: it overlaps the tail of the previous kernel in the stream (PDL)
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) p.trace[12 * 512 + 1] = clock64();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_work = num_tiles * p.split_k;
@@ -596,6 +601,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
+  }
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    if (blockIdx.x == 0) { p.trace[12 * 512 + 2] = clock64(); p.trace[13 * 512 + 1] = (long long)global_timer_ns(); }
+    atomicMax(reinterpret_cast<unsigned long long*>(p.trace + 15 * 512), global_timer_ns());
   }
 }
 
