@@ -602,7 +602,7 @@ def run(args) -> dict:
         torch.cuda.empty_cache()
     final_loss, final_tokens = evaluate_model(stepper, eval_loader, device, target_eval_tokens=100_000_000)
     result = {"final_eval_loss": float(final_loss), "final_eval_tokens": final_tokens, "update_step": st.update_step,
-              "global_step": st.global_step, "last_train_loss": last_loss, "save_dir": args.save_dir,
+              "global_step": st.global_step, "tokens_seen": st.tokens_seen, "last_train_loss": last_loss, "save_dir": args.save_dir,
               "n_lora_restarts": st.n_lora_restarts, "n_optimizer_resets": st.n_optimizer_resets,
               "executor": type(stepper).__name__}
     if rank == 0:
