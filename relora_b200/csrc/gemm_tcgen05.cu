@@ -188,7 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   if constexpr (PAIR) cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
   else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);  // known warp-uniform: stays in a uniform register
   pdl_wait();  // everything above is CTA-local: it overlaps the tail of the previous kernel in the stream (PDL)
   if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) p.trace[12 * 512 + 1] = clock64();
 
@@ -200,31 +200,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
   const int num_kb = kb1 + kb2;
   const int kb_per_split = (num_kb + p.split_k - 1) / p.split_k;
 
+  // Producer and MMA issuer: the WHOLE warp walks the loop with uniform control flow and one elected lane issues.  Under an
+  // `if (lane == 0)` branch ptxas cannot prove addresses / descriptors warp-uniform and wraps every UTMALDG / UTCHMMA in an
+  // ELECT + R2UR + BRA.U.ANY loop: ~100-130 dependent instructions per k-block on one warp = a ~600-cycle floor per k-block
+  // (what capped 128-wide tiles at ~45 % and 256-wide tiles at ~83 % of the tensor peak).  Converged, the same loop is ~50
+  // uniform-datapath instructions with the four UTCHMMA back to back.
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int tr_p = 0;
-      const uint32_t full_addr0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-      const int b_half = PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0;  // this CTA's share of the B tile
-      for (int work = work0; work < num_work; work += work_step) {
-        const int tile = work / p.split_k, split = work % p.split_k;
-        const int m0 = (tile / p.num_n_tiles) * kTileM + (int)cta_rank * BLOCK_M;
-        const int tn = tile % p.num_n_tiles;
-        const int g = tn / p.tiles_per_group;
-        const int nl = (tn % p.tiles_per_group) * BLOCK_N;  // column offset inside the group
-        const int n0 = g * p.n_per_group + nl;
-        const int a1_k = g * p.a1_group_kofs;
-        const int a2_k = g * p.a2_group_kofs;
-        const int b1_k = g * p.b1_group_kofs;
-        const int b1_n = (p.b1_local_n ? nl : n0) + (m0 / p.m_per_group) * p.b1_mn_ofs_per_mgroup;
-        const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int tr_p = 0;
+    const uint32_t full_addr0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+    const int b_half = PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0;  // this CTA's share of the B tile
+    for (int work = work0; work < num_work; work += work_step) {
+      const int tile = work / p.split_k, split = work % p.split_k;
+      const int m0 = (tile / p.num_n_tiles) * kTileM + (int)cta_rank * BLOCK_M;
+      const int tn = tile % p.num_n_tiles;
+      const int g = tn / p.tiles_per_group;
+      const int nl = (tn % p.tiles_per_group) * BLOCK_N;  // column offset inside the group
+      const int n0 = g * p.n_per_group + nl;
+      const int a1_k = g * p.a1_group_kofs;
+      const int a2_k = g * p.a2_group_kofs;
+      const int b1_k = g * p.b1_group_kofs;
+      const int b1_n = (p.b1_local_n ? nl : n0) + (m0 / p.m_per_group) * p.b1_mn_ofs_per_mgroup;
+      const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          if (p.trace != nullptr && blockIdx.x == 0 && tr_p < 512) p.trace[0 * 512 + tr_p++] = clock64();
+          if (p.trace != nullptr && blockIdx.x == 0 && tr_p < 512) p.trace[0 * 512 + tr_p] = clock64();
           const uint32_t fb = full_addr0 + stage * 8;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * L::kStageBytes);  // both CTAs' bytes land here
           if (kb < kb1) {
@@ -235,19 +240,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
             load_operand<BLOCK_M, false, PAIR>(&map_a2, fb, sa, m0, a2_k + k, kEvictNormal);
             load_operand<L::kBRows, false, PAIR>(&map_b2, fb, sb, n0 + b_half, k, kEvictLast);
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        ++tr_p;
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc1 = make_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t idesc2 = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
       const uint32_t idesc8 = p.fp8 == 2 ? make_idesc_e4m3(kTileM, BLOCK_N, 1) : make_idesc_e4m3(kTileM, BLOCK_N, 0);
+      // descriptor of k-step 0 + (byte offset >> 4) in the 14-bit start-address field: 32 B per K = 16 step of a K-major
+      // tile (also E4M3, K = 32), 2048 B (16 rows of 128 B) per step of an MN-major tile; shared memory is < 256 KB: no carry
+      constexpr uint64_t kStepA = A_MN ? 128 : 2, kStepB = B_MN ? 128 : 2;
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_flag) {
         if constexpr (PAIR) umma_f16_ss_pair(d, da, db, idesc, acc_flag);
         else umma_f16_ss(d, da, db, idesc, acc_flag);
@@ -260,6 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         if constexpr (PAIR) umma_commit_pair(bar, 3);
         else umma_commit(bar);
       };
+      const uint32_t smem0 = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -270,35 +281,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ 
         const int kb_begin = split * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (p.trace != nullptr && blockIdx.x == 0 && tr_t < 512) p.trace[2 * 512 + tr_t] = clock64();
+        if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_t < 512) p.trace[2 * 512 + tr_t] = clock64();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (p.trace != nullptr && blockIdx.x == 0 && tr_m < 512) p.trace[1 * 512 + tr_m++] = clock64();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_m < 512) p.trace[1 * 512 + tr_m] = clock64();
+          ++tr_m;
+          const uint32_t sa = smem0 + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
-          if (kb < kb1 && p.fp8) {  // E4M3 rows of 128 bytes: four K = 32 steps, same byte offsets as bf16
+          if (elect_one()) {
+            if (kb < kb1 && p.fp8) {  // E4M3 rows of 128 bytes: four K = 32 steps, same byte offsets as bf16
+              const uint64_t da = operand_desc<false>(sa, 0), db = operand_desc<false>(sb, 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma8(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), ((kb - kb_begin) | k) != 0);
-          } else if (kb < kb1) {
+              for (int k = 0; k < 4; ++k) mma8(d_tmem, da + 2 * k, db + 2 * k, ((kb - kb_begin) | k) != 0);
+            } else if (kb < kb1) {
+              const uint64_t da = operand_desc<A_MN>(sa, 0), db = operand_desc<B_MN>(sb, 0);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              mma(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc1, ((kb - kb_begin) | k) != 0);
-          } else {
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(d_tmem, da + kStepA * k, db + kStepB * k, idesc1, ((kb - kb_begin) | k) != 0);
+            } else {
+              const uint64_t da = operand_desc<false>(sa, 0), db = operand_desc<false>(sb, 0);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              mma(d_tmem, operand_desc<false>(sa, k), operand_desc<false>(sb, k), idesc2, ((kb - kb_begin) | k) != 0);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(d_tmem, da + 2 * k, db + 2 * k, idesc2, ((kb - kb_begin) | k) != 0);
+            }
+            commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           }
-          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue(s)
-        if (p.trace != nullptr && blockIdx.x == 0 && tr_t < 512) p.trace[3 * 512 + tr_t++] = clock64();
+        if (elect_one()) commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue(s)
+        __syncwarp();
+        if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_t < 512) p.trace[3 * 512 + tr_t] = clock64();
+        ++tr_t;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -1025,7 +1042,7 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
   pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -1033,8 +1050,8 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
   const int kb_base = (p.Kb + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (whole warp, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
@@ -1048,25 +1065,31 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
         for (int kb = 0; kb < G * kb_lora; ++kb) {  // du [M, G·r] K-major ; A [G·r, N] MN-major
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          }
+          __syncwarp();
           advance();
         }
         for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_dy, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_w, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            load_operand<BLOCK_M, false>(&map_dy, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N, true>(&map_w, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          }
+          __syncwarp();
           advance();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -1075,12 +1098,15 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
       auto mma_block = [&](uint32_t d_tmem, bool first) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sa = smem_u32(smem) + stage * L::kStageBytes;
         const uint32_t sb = sa + L::kABytes;
+        if (elect_one()) {
+          const uint64_t da = operand_desc<false>(sa, 0), db = operand_desc<true>(sb, 0);  // + (byte offset >> 4) per K = 16 step
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(first && k == 0));
-        umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 128 * k, idesc, !(first && k == 0));
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -1093,13 +1119,15 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
           const uint32_t d_tmem = tmem_base + (kBaseStages + ls * G + g) * BLOCK_N;
           for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
         }
-        umma_commit(&lora_full[ls]);
+        if (elect_one()) umma_commit(&lora_full[ls]);
+        __syncwarp();
         if (kb_base > 0) {
           mbar_wait(&base_empty[bs], bs_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
           for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
-          umma_commit(&base_full[bs]);
+          if (elect_one()) umma_commit(&base_full[bs]);
+          __syncwarp();
         }
         if (++ls == kLoraStages) {
           ls = 0;
@@ -1218,6 +1246,283 @@ lora_dx_fused2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
   }
 }
 
+// CTA-pair form of the one-kernel LoRA input gradient (cta_group::2): a pair owns a 256 x 128 tile, each CTA stages its own 128
+// rows of dy / du and only HALF (64 columns) of the W / A tile: 24 KB instead of 32 KB per k-block, and EIGHT stages instead of five.
+// The 128-wide kernels are bound by load latency, not by bandwidth or the epilogue: a k-block costs ~640 cycles whatever the tile does
+// (ncu: tensor pipe 35 %, L2 -> SM 35 % of peak; pair tiles with 5 stages, or 4 epilogue warpgroups, change nothing), which is
+// 5 stages / ~3 k cycles of loaded TMA latency.  More k-blocks in flight is what moves it.  MMAs are issued by the leader CTA; both
+// CTAs run their own producer and their own two epilogue warpgroups (one output slab each) on their own rows of the accumulator.
+struct LoraPairSmem {
+  static constexpr int kStages = 8;
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;        // 16 KB: this CTA's 128 rows of dy / du
+  static constexpr int kBBytes = 64 * BLOCK_K * 2;             // 8 KB: this CTA's 64 columns of W / A
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTileBytes = kStages * kStageBytes;     // 192 KB
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kSlabBytes = BLOCK_M * 128;
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + 2 * kSlabBytes + 1024;
+};
+static_assert(LoraPairSmem::kTotal <= 232448, "shared memory budget");
+template <int G>
+__global__ void __launch_bounds__(384, 1)
+lora_dx_pair_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_a,
+               const __grid_constant__ CUtensorMap map_out, const LoraDxArgs p) {
+  constexpr int BLOCK_N = 128;
+  using L = LoraPairSmem;
+  constexpr int kStages = L::kStages;
+  constexpr int kBaseStages = (G <= 2) ? 2 : 1;  // TMEM budget: (kBaseStages + kLoraStages·G) · 128 <= 512 columns
+  constexpr int kLoraStages = (G == 1) ? 2 : 1;
+  constexpr uint32_t kTmemCols = 512;
+  static_assert((kBaseStages + kLoraStages * G) * BLOCK_N <= 512, "tensor memory budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* lora_full = empty_bar + kStages;
+  uint64_t* lora_empty = lora_full + 2;
+  uint64_t* base_full = lora_empty + 2;
+  uint64_t* base_empty = base_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(base_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int work0 = (int)cluster_id_x(), work_step = (int)cluster_count_x();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_du);
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&lora_full[a], 1);
+      mbar_init(&lora_empty[a], 512);  // the epilogue threads of BOTH CTAs release the leader's accumulators
+      mbar_init(&base_full[a], 1);
+      mbar_init(&base_empty[a], 512);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_base_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
+  pdl_wait();
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_lora = p.r / BLOCK_K;                     // r is a multiple of 64
+  const int kb_base = (p.Kb + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (whole warp, one elected lane issues)
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_addr0 = mapa_shared(smem_u32(&full_bar[0]), 0);  // loads of both CTAs complete on the leader's barrier
+      const int b_half = (int)cta_rank * (BLOCK_N / 2);
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = work0; tile < num_tiles; tile += work_step) {
+        const int m0 = (tile / p.num_n_tiles) * 2 * BLOCK_M + (int)cta_rank * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N + b_half;
+        for (int kb = 0; kb < G * kb_lora; ++kb) {  // du [M, G·r] K-major ; A [G·r, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            load_operand<BLOCK_M, false, true>(&map_du, full_addr0 + stage * 8, sa, m0, kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N / 2, true, true>(&map_a, full_addr0 + stage * 8, sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          }
+          __syncwarp();
+          advance();
+        }
+        for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            load_operand<BLOCK_M, false, true>(&map_dy, full_addr0 + stage * 8, sa, m0, kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N / 2, true, true>(&map_w, full_addr0 + stage * 8, sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          }
+          __syncwarp();
+          advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (whole warp of the leader CTA, one elected lane issues)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, 0, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ls = 0, bs = 0;
+      uint32_t ls_phase = 0, bs_phase = 0;
+      auto mma_block = [&](uint32_t d_tmem, bool first) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem) + stage * L::kStageBytes;
+        const uint32_t sb = sa + L::kABytes;
+        if (elect_one()) {
+          const uint64_t da = operand_desc<false>(sa, 0), db = operand_desc<true>(sb, 0);  // + (byte offset >> 4) per K = 16 step
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16_ss_pair(d_tmem, da + 2 * k, db + 128 * k, idesc, !(first && k == 0));
+          umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = work0; tile < num_tiles; tile += work_step) {
+        mbar_wait(&lora_empty[ls], ls_phase ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g) {
+          const uint32_t d_tmem = tmem_base + (kBaseStages + ls * G + g) * BLOCK_N;
+          for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
+        }
+        if (elect_one()) umma_commit_pair(&lora_full[ls], 3);
+        __syncwarp();
+        if (kb_base > 0) {
+          mbar_wait(&base_empty[bs], bs_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
+          for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
+          if (elect_one()) umma_commit_pair(&base_full[bs], 3);
+          __syncwarp();
+        }
+        if (++ls == kLoraStages) {
+          ls = 0;
+          ls_phase ^= 1;
+        }
+        if (++bs == kBaseStages) {
+          bs = 0;
+          bs_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================================================================== epilogue: warps 4-7 -> columns 0-63, warps 8-11 -> 64-127
+    // (the single-warpgroup epilogue was ~3x longer than the tile's MMAs at K = 768: ncu, profiles/ncu/lora_dx_k2560_g1_round2)
+    const uint32_t quad = warp & 3;
+    const uint32_t half = (warp - kEpilogueWarp0) >> 2;
+    const bool issuer = ((warp & 3) == 0) && lane == 0;
+    uint8_t* slab = smem + L::kTileBytes + L::kBarrierBytes + half * L::kSlabBytes;  // one private slab per warpgroup
+    const uint32_t seed0 = p.seed_ptr ? *p.seed_ptr : 0u;
+    uint32_t seeds[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) seeds[g] = mix_seed(seed0, p.keys[g]);
+    int ls = 0, bs = 0;
+    uint32_t ls_phase = 0, bs_phase = 0;
+    const uint32_t lora_empty0 = mapa_shared(smem_u32(&lora_empty[0]), 0), base_empty0 = mapa_shared(smem_u32(&base_empty[0]), 0);
+    for (int tile = work0; tile < num_tiles; tile += work_step) {
+      const int m0 = (tile / p.num_n_tiles) * 2 * BLOCK_M + (int)cta_rank * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N + half * 64;
+      const uint32_t rloc = quad * 32 + lane;
+      const uint32_t row = m0 + rloc;
+      const uint32_t rowmix = row * 0x9E3779B1u;
+      // ---- phase 1: masked sum of this half's LoRA accumulator columns, packed to bf16x2 (overlaps the frozen-path MMAs)
+      uint32_t cpk[32];
+      mbar_wait(&lora_full[ls], ls_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float cf[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf[i] = 0.f;
+        uint32_t rr[G][16];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + half * 64 + c4 * 16), rr[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint32_t sg = rowmix ^ seeds[g];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {  // one hash per column pair (common.cuh:keep_drop)
+            const uint32_t cp = (uint32_t)(n0 + c4 * 16 + i) >> 1;
+            const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
+            if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[g][i]);
+            if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[g][i + 1]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cpk[c4 * 8 + i] = pack_bf16x2(cf[2 * i] * p.inv_keep, cf[2 * i + 1] * p.inv_keep);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(lora_empty0 + ls * 8);
+      // ---- phase 2: frozen-path accumulator (this half's 64 columns) + combined LoRA term -> bf16 slab -> TMA store
+      mbar_wait(&base_full[bs], bs_phase);
+      tc_fence_after();
+      uint8_t* rowp = slab + rloc * 128;
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + half * 64), r0);
+        tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + half * 64 + 32), r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(base_empty0 + bs * 8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float2 c2 = unpack_bf16x2(cpk[q * 4 + i / 2]);
+            const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
+            const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
+            f[i] = __uint_as_float(raw0) + c2.x;
+            f[i + 1] = __uint_as_float(raw1) + c2.y;
+          }
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = pack8(f);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (issuer) {
+        if (n0 < p.N) {
+          tma_store_2d(&map_out, slab, n0, m0);
+          tma_store_commit();
+        }
+        tma_store_wait_read<0>();  // the slab is rewritten for the next tile after the barrier below
+      }
+      named_bar_sync(1 + half, 128);
+      if (++ls == kLoraStages) {
+        ls = 0;
+        ls_phase ^= 1;
+      }
+      if (++bs == kBaseStages) {
+        bs = 0;
+        bs_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still read this CTA's shared memory / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // =============================================================================================
 // Two-kernel form of the LoRA input gradient with the frozen-path product supplied (`base`):
 //
@@ -1274,14 +1579,14 @@ lora_dx_base_kernel(const __grid_constant__ CUtensorMap map_du, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
   pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_lora = p.r / BLOCK_K;
 
   if (warp == 0) {
-    if (lane == 0) {  // TMA producer: du [M, G·r] K-major ; A [G·r, N] MN-major
+    {  // TMA producer (whole warp, one elected lane issues): du [M, G·r] K-major ; A [G·r, N] MN-major
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -1289,10 +1594,13 @@ lora_dx_base_kernel(const __grid_constant__ CUtensorMap map_du, const __grid_con
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
         for (int kb = 0; kb < G * kb_lora; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
+            load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -1301,7 +1609,7 @@ lora_dx_base_kernel(const __grid_constant__ CUtensorMap map_du, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // MMA issuer
+    {  // MMA issuer (whole warp, one elected lane issues)
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
       int stage = 0, ls = 0;
       uint32_t phase = 0, ls_phase = 0;
@@ -1313,19 +1621,23 @@ lora_dx_base_kernel(const __grid_constant__ CUtensorMap map_du, const __grid_con
           for (int kb = 0; kb < kb_lora; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sa = smem_u32(smem) + stage * L::kStageBytes;
             const uint32_t sb = sa + L::kABytes;
+            if (elect_one()) {
+              const uint64_t da = operand_desc<false>(sa, 0), db = operand_desc<true>(sb, 0);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(kb == 0 && k == 0));
-            umma_commit(&empty_bar[stage]);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 128 * k, idesc, !(kb == 0 && k == 0));
+              umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        umma_commit(&lora_full[ls]);
+        if (elect_one()) umma_commit(&lora_full[ls]);
+        __syncwarp();
         if (++ls == kLoraStages) {
           ls = 0;
           ls_phase ^= 1;
@@ -1715,6 +2027,46 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
     const char* e = getenv("RB_LORA_DX_SPLIT");  // 0: single epilogue warpgroup (the round-1 kernel; A/B timing)
     return e == nullptr || atoi(e) != 0;
   }();
+  static const bool pair_ok = [] {
+    const char* e = getenv("RB_LORA_DX_PAIR");  // 0: single-CTA 128 x 128 tiles, 5 stages (lora_dx_fused2_kernel; A/B timing)
+    return e == nullptr || atoi(e) != 0;
+  }();
+  // measured with the converged issue loops (bench/lora_dx_bench.py): pairs win from a reduction of ~2 K up (1b down dx 145 vs 156 us,
+  // 250m qkv dx 45.5 vs 48.7), single CTAs below (250m down dx, Kb = 768: 55.8 vs 66.2 us)
+  if (d.Kb >= 1536 && split && pair_ok && d.M > BLOCK_M) {
+    using LP = LoraPairSmem;
+    auto kernp = lora_dx_pair_kernel<G>;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      check(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal), "cudaFuncSetAttribute(lora_dx_pair)");
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms() / 2 * 2); qc.blockDim = dim3(384); qc.dynamicSmemBytes = LP::kTotal;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernp, &qc) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms() / 2;
+      }
+      max_clusters = n;
+    }
+    p.num_m_tiles = ceil_div(d.M, 2 * BLOCK_M);  // one 256-row tile per CTA pair
+    const int ptiles = p.num_m_tiles * p.num_n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (ptiles < max_clusters ? ptiles : max_clusters)); cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = LP::kTotal; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    check(cudaLaunchKernelEx(&cfg, kernp, m_dy, m_w, m_du, m_a, m_out, p), "cudaLaunchKernelEx(lora_dx pair)");
+    RB_CHECK_LAUNCH("lora_dx_pair_kernel");
+    return;
+  }
   if (d.Kb > 0 && split) {
     auto kern2 = lora_dx_fused2_kernel<G>;
     static bool configured2 = false;

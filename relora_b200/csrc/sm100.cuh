@@ -253,17 +253,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
+  return __shfl_sync(0xffffffffu, r, 0);  // same value in every lane: lets ptxas keep dependent addresses in uniform registers
 }
 __device__ __forceinline__ uint32_t cluster_id_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-  return r;
+  return __shfl_sync(0xffffffffu, r, 0);  // same value in every lane: lets ptxas keep dependent addresses in uniform registers
 }
 __device__ __forceinline__ uint32_t cluster_count_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-  return r;
+  return __shfl_sync(0xffffffffu, r, 0);  // same value in every lane: lets ptxas keep dependent addresses in uniform registers
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
