@@ -64,6 +64,15 @@ __device__ __forceinline__ void attn_wait(uint64_t* bar, uint32_t parity) {
   else mbar_wait(bar, parity);
 }
 
+// The control warp walks its loop with all 32 lanes (uniform control flow: ptxas keeps shared-memory addresses, descriptors and TMEM
+// addresses in uniform registers) and ONE elected lane issues the TMA / tcgen05 instructions.  Under an `if (lane == 0)` branch
+// every UTMALDG / UTCHMMA is wrapped in an ELECT + R2UR + BRA.U.ANY loop (~17 extra dependent instructions per MMA).
+#define RB_ONE_LANE(...)          \
+  do {                            \
+    if (elect_one()) { __VA_ARGS__ } \
+    __syncwarp();                 \
+  } while (0)
+
 __device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2, no range fix-up (inputs are <= ~8, -inf -> 0)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -129,7 +138,7 @@ struct FwdArgs {
 // =============================================================================================== forward
 __global__ void __launch_bounds__((4 * kFwdGroups + kFwdGroups) * 32, kFwdGroups == 1 ? 3 : 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdArgs p) {
   constexpr int NG = kFwdGroups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp index known uniform to ptxas
   if (threadIdx.x == 0) pdl_launch_dependents();
   const bool is_ctrl = warp >= 4 * NG;
   const int g = is_ctrl ? warp - 4 * NG : warp >> 2;  // group of this warp
@@ -180,27 +189,28 @@ __global__ void __launch_bounds__((4 * kFwdGroups + kFwdGroups) * 32, kFwdGroups
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot + g * 128;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0) + g * 128;
   pdl_wait();
 
   if (is_ctrl) {
-    if (lane == 0 && active) {
+    if (active) {
       auto load_kv = [&](int jj, int st) {
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
-        tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
-        tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK);
+        RB_ONE_LANE(mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
+                    tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
+                    tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK););
       };
-      mbar_arrive_expect_tx(q_full, kTile128);
-      tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
-      tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64);
+      RB_ONE_LANE(mbar_arrive_expect_tx(q_full, kTile128);
+                  tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
+                  tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64););
       load_kv(0, 0);
       if (n_kv > 1) load_kv(1, 1);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       auto issue_s = [&](int st) {
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_s, k != 0);
-        umma_commit(s_full);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_s, k != 0);
+            umma_commit(s_full););
       };
       attn_wait(q_full, 0);
       attn_wait(&kv_full[0], 0);
@@ -217,11 +227,12 @@ __global__ void __launch_bounds__((4 * kFwdGroups + kFwdGroups) * 32, kFwdGroups
           tc_fence_after();
           issue_s(st ^ 1);
         }
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + 64, desc_k(sP, k), desc_mn(sV + st * kTile64, k), idesc_pv, (jj | k) != 0);  // O accumulates in TMEM
-        umma_commit(o_full);
-        umma_commit(&kv_free[st]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + 64, desc_k(sP, k), desc_mn(sV + st * kTile64, k), idesc_pv, (jj | k) != 0);  // O accumulates in TMEM
+            umma_commit(o_full);
+            umma_commit(&kv_free[st]););
         if (jj + 2 < n_kv) {
           attn_wait(&kv_free[st], (jj >> 1) & 1);
           load_kv(jj + 2, st);
@@ -389,7 +400,7 @@ struct BwdArgs {
 __global__ void __launch_bounds__((kBwdRowWarps * kDqGroups + kDqGroups) * 32, kDqGroups == 1 ? 2 : 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                    const __grid_constant__ CUtensorMap map_do, const BwdArgs p) {
   constexpr int NG = kDqGroups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp index known uniform to ptxas
   if (threadIdx.x == 0) pdl_launch_dependents();
   const bool is_ctrl = warp >= kBwdRowWarps * NG;
   const int g = is_ctrl ? warp - kBwdRowWarps * NG : warp / kBwdRowWarps;  // group of this warp
@@ -441,31 +452,32 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDqGroups + kDqGroups) * 32, k
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot + g * 256;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0) + g * 256;
   pdl_wait();
 
   if (is_ctrl) {
-    if (lane == 0 && active) {
+    if (active) {
       auto load_kv = [&](int jj, int st) {
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
-        tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
-        tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK);
+        RB_ONE_LANE(mbar_arrive_expect_tx(&kv_full[st], 2 * kTile64);
+                    tma_load_3d(&map_qkv, &kv_full[st], sK + st * kTile64, 0, p.nh + head, row0 + jj * BK);
+                    tma_load_3d(&map_qkv, &kv_full[st], sV + st * kTile64, 0, 2 * p.nh + head, row0 + jj * BK););
       };
-      mbar_arrive_expect_tx(q_full, 2 * kTile128);
-      tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
-      tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64);
-      tma_load_3d(&map_do, q_full, sdO, 0, head, row0 + t0);
-      tma_load_3d(&map_do, q_full, sdO + kTile64, 0, head, row0 + t0 + 64);
+      RB_ONE_LANE(mbar_arrive_expect_tx(q_full, 2 * kTile128);
+                  tma_load_3d(&map_qkv, q_full, sQ, 0, head, row0 + t0);
+                  tma_load_3d(&map_qkv, q_full, sQ + kTile64, 0, head, row0 + t0 + 64);
+                  tma_load_3d(&map_do, q_full, sdO, 0, head, row0 + t0);
+                  tma_load_3d(&map_do, q_full, sdO + kTile64, 0, head, row0 + t0 + 64););
       load_kv(0, 0);
       if (n_kv > 1) load_kv(1, 1);
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, 0, 1);
       auto issue_sdp = [&](int st) {
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_kk, k != 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sQ, k), desc_k(sK + st * kTile64, k), idesc_kk, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sdO, k), desc_k(sV + st * kTile64, k), idesc_kk, k != 0);
-        umma_commit(sdp_full);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sdO, k), desc_k(sV + st * kTile64, k), idesc_kk, k != 0);
+            umma_commit(sdp_full););
       };
       attn_wait(q_full, 0);
       attn_wait(&kv_full[0], 0);
@@ -475,16 +487,17 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDqGroups + kDqGroups) * 32, k
         const int st = jj & 1;
         attn_wait(ds_ready, jj & 1);
         tc_fence_after();
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + 128, desc_k(sdS, k), desc_mn(sK + st * kTile64, k), idesc_kmn, (jj | k) != 0);
-        umma_commit(&kv_free[st]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + 128, desc_k(sdS, k), desc_mn(sK + st * kTile64, k), idesc_kmn, (jj | k) != 0);
+            umma_commit(&kv_free[st]););
         if (jj + 1 < n_kv) {
           attn_wait(&kv_full[st ^ 1], ((jj + 1) >> 1) & 1);
           tc_fence_after();
           issue_sdp(st ^ 1);  // its commit also covers the dQ MMAs above: dS may be overwritten once sdp_full fires
         } else {
-          umma_commit(dq_full);
+          RB_ONE_LANE(umma_commit(dq_full););
         }
         if (jj + 2 < n_kv) {
           attn_wait(&kv_free[st], (jj >> 1) & 1);
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
                                                                     const __grid_constant__ CUtensorMap map_do,
                                                                     const __grid_constant__ CUtensorMap map_ds, const BwdArgs p) {
   constexpr int NG = kDkvGroups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp index known uniform to ptxas
   if (threadIdx.x == 0) pdl_launch_dependents();
   const bool is_ctrl = warp >= kBwdRowWarps * NG;
   const int g = is_ctrl ? warp - kBwdRowWarps * NG : warp / kBwdRowWarps;  // group of this warp
@@ -606,31 +619,32 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot + g * 256;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0) + g * 256;
   pdl_wait();
 
   if (is_ctrl) {
-    if (lane == 0 && active) {
+    if (active) {
       auto load_q = [&](int ii, int st) {
-        mbar_arrive_expect_tx(&q_full[st], 2 * kTile64);
-        tma_load_3d(&map_qkv, &q_full[st], sQ + st * kTile64, 0, head, row0 + kstart + ii * BK);
-        tma_load_3d(&map_do, &q_full[st], sdO + st * kTile64, 0, head, row0 + kstart + ii * BK);
+        RB_ONE_LANE(mbar_arrive_expect_tx(&q_full[st], 2 * kTile64);
+                    tma_load_3d(&map_qkv, &q_full[st], sQ + st * kTile64, 0, head, row0 + kstart + ii * BK);
+                    tma_load_3d(&map_do, &q_full[st], sdO + st * kTile64, 0, head, row0 + kstart + ii * BK););
       };
-      mbar_arrive_expect_tx(kv_full, 2 * kTile128);
-      tma_load_3d(&map_qkv, kv_full, sK, 0, p.nh + head, row0 + kstart);
-      tma_load_3d(&map_qkv, kv_full, sK + kTile64, 0, p.nh + head, row0 + kstart + 64);
-      tma_load_3d(&map_qkv, kv_full, sV, 0, 2 * p.nh + head, row0 + kstart);
-      tma_load_3d(&map_qkv, kv_full, sV + kTile64, 0, 2 * p.nh + head, row0 + kstart + 64);
+      RB_ONE_LANE(mbar_arrive_expect_tx(kv_full, 2 * kTile128);
+                  tma_load_3d(&map_qkv, kv_full, sK, 0, p.nh + head, row0 + kstart);
+                  tma_load_3d(&map_qkv, kv_full, sK + kTile64, 0, p.nh + head, row0 + kstart + 64);
+                  tma_load_3d(&map_qkv, kv_full, sV, 0, 2 * p.nh + head, row0 + kstart);
+                  tma_load_3d(&map_qkv, kv_full, sV + kTile64, 0, 2 * p.nh + head, row0 + kstart + 64););
       load_q(0, 0);
       if (n_q > 1) load_q(1, 1);
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, 0, 1);
       auto issue_sdp = [&](int st) {
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sK, k), desc_k(sQ + st * kTile64, k), idesc_kk, k != 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, desc_k(sK, k), desc_k(sQ + st * kTile64, k), idesc_kk, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sV, k), desc_k(sdO + st * kTile64, k), idesc_kk, k != 0);
-        umma_commit(sdp_full);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + 64, desc_k(sV, k), desc_k(sdO + st * kTile64, k), idesc_kk, k != 0);
+            umma_commit(sdp_full););
       };
       attn_wait(kv_full, 0);
       attn_wait(&q_full[0], 0);
@@ -640,27 +654,31 @@ __global__ void __launch_bounds__((kBwdRowWarps * kDkvGroups + kDkvGroups) * 32,
         const int st = ii & 1;
         attn_wait(pds_ready, ii & 1);
         tc_fence_after();
+        RB_ONE_LANE(
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + 128, desc_k(sPt, k), desc_mn(sdO + st * kTile64, k), idesc_kmn, (ii | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + 128, desc_k(sPt, k), desc_mn(sdO + st * kTile64, k), idesc_kmn, (ii | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + 192, desc_k(sdSt, k), desc_mn(sQ + st * kTile64, k), idesc_kmn, (ii | k) != 0);
-        umma_commit(&q_free[st]);
-        if (p.store_ds) {
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + 192, desc_k(sdSt, k), desc_mn(sQ + st * kTile64, k), idesc_kmn, (ii | k) != 0);
+            umma_commit(&q_free[st]););
+        if (p.store_ds && lane == 0) {  // bulk-store groups are per thread: lane 0 stores, commits and waits
           // dSᵀ tile [128 keys x 64 queries] -> global [b*nh+head][key][query]: the dQ kernel then is a plain TMA -> MMA pipeline
           // (dQ = dS·K) instead of recomputing S and dP (the row threads fenced their writes before arriving on pds_ready)
           tma_store_3d(&map_ds, sdSt, kstart + ii * BK, kstart, b * p.nh + head);
           tma_store_commit();
         }
+        __syncwarp();
         if (ii + 1 < n_q) {
           attn_wait(&q_full[st ^ 1], ((ii + 1) >> 1) & 1);
           tc_fence_after();
-          if (p.store_ds) tma_store_wait_read<0>();  // the next step's row threads overwrite the tile once sdp_full fires
+          if (p.store_ds && lane == 0) tma_store_wait_read<0>();  // the next step's row threads overwrite the tile once sdp_full fires
+          __syncwarp();
           issue_sdp(st ^ 1);
         } else {
-          umma_commit(acc_full);
-          if (p.store_ds) tma_store_wait<0>();
+          RB_ONE_LANE(umma_commit(acc_full););
+          if (p.store_ds && lane == 0) tma_store_wait<0>();
+          __syncwarp();
         }
         if (ii + 2 < n_q) {
           attn_wait(&q_free[st], (ii >> 1) & 1);
@@ -752,7 +770,7 @@ constexpr int kDq2StageBytes = 2 * kTile128 + 2 * kTile64;   // dSᵀ (two 64-qu
 constexpr int kDq2Smem = 2 * kDq2StageBytes + 1024 + 1024;
 __global__ void __launch_bounds__(160, 2) attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_ds,
                                                               const BwdArgs p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp index known uniform to ptxas
   const bool is_ctrl = warp >= 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -788,20 +806,20 @@ __global__ void __launch_bounds__(160, 2) attn_bwd_dq2_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();
 
   if (is_ctrl) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
       auto load = [&](int kb, int st) {
         uint8_t* sA = smem + st * kDq2StageBytes;
         uint8_t* sB = sA + 2 * kTile128;
-        mbar_arrive_expect_tx(&full[st], kDq2StageBytes);
-        tma_load_3d(&map_ds, &full[st], sA, t0, kb * BQ, b * p.nh + head);
-        tma_load_3d(&map_ds, &full[st], sA + kTile128, t0 + 64, kb * BQ, b * p.nh + head);
-        tma_load_3d(&map_qkv, &full[st], sB, 0, p.nh + head, row0 + kb * BQ);
-        tma_load_3d(&map_qkv, &full[st], sB + kTile64, 0, p.nh + head, row0 + kb * BQ + 64);
+        RB_ONE_LANE(mbar_arrive_expect_tx(&full[st], kDq2StageBytes);
+                    tma_load_3d(&map_ds, &full[st], sA, t0, kb * BQ, b * p.nh + head);
+                    tma_load_3d(&map_ds, &full[st], sA + kTile128, t0 + 64, kb * BQ, b * p.nh + head);
+                    tma_load_3d(&map_qkv, &full[st], sB, 0, p.nh + head, row0 + kb * BQ);
+                    tma_load_3d(&map_qkv, &full[st], sB + kTile64, 0, p.nh + head, row0 + kb * BQ + 64););
       };
       load(0, 0);
       if (n_kb > 1) load(1, 1);
@@ -810,17 +828,18 @@ __global__ void __launch_bounds__(160, 2) attn_bwd_dq2_kernel(const __grid_const
         attn_wait(&full[st], (kb >> 1) & 1);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + st * kDq2StageBytes), sB = sA + 2 * kTile128;
+        RB_ONE_LANE(
+            const uint64_t da = make_desc_sw128(sA, kTile128, 1024); const uint64_t db = make_desc_sw128(sB, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // 16 keys per instruction; A: query chunks of 64 are 16 KB apart, 8-key groups 1 KB apart
-          umma_f16_ss(tmem_base, make_desc_sw128(sA + k * 2048, kTile128, 1024), make_desc_sw128(sB + k * 2048, 8192, 1024), idesc,
-                      (kb | k) != 0);
-        umma_commit(&free_[st]);
+            for (int k = 0; k < 8; ++k)  // 16 keys per instruction (2048 B = +128 in the start-address field); A: query chunks of 64 are
+              umma_f16_ss(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0);  // 16 KB apart, 8-key groups 1 KB apart
+            umma_commit(&free_[st]););
         if (kb + 2 < n_kb) {
           attn_wait(&free_[st], (kb >> 1) & 1);
           load(kb + 2, st);
         }
       }
-      umma_commit(done);
+      RB_ONE_LANE(umma_commit(done););
     }
   } else {
     const int r = threadIdx.x & 127;

@@ -143,14 +143,16 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // known warp-uniform
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb8 = p.K8 / KB8, kb16 = p.K2 / KB16;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer: the whole warp walks the loop, one elected lane
+    // issues (uniform control flow lets ptxas keep addresses / descriptors in uniform registers instead of wrapping every
+    // UTMALDG / UTC*MMA in an ELECT + R2UR + BRA.U.ANY loop; see gemm_tcgen05.cu)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -160,7 +162,8 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kTileBytes;
-          if (kb < kb8) {
+          if (!elect_one()) {
+          } else if (kb < kb8) {
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes + 2 * kSfBytes);
             tma_load_2d(&map_a, &full_bar[stage], sa, kb * KB8, m0, kEvictNormal);
             if constexpr (B_MN) tma_load_2d(&map_b, &full_bar[stage], sb, n0, kb * KB8, kEvictLast);  // box {128 (MN), 128 (K rows)}
@@ -174,6 +177,7 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_2d(&map_a2, &full_bar[stage], sa, k, m0, kEvictNormal);
             tma_load_2d(&map_b2, &full_bar[stage], sb, k, n0, kEvictLast);
           }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -182,8 +186,8 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t idesc16 = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0, acc = 0, sfbuf = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -194,9 +198,10 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < kb8 + kb16; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = smem_u32(smem) + stage * kStageBytes;
           const uint32_t sb = sa + kTileBytes;
-          if (kb < kb8) {
+          if (!elect_one()) {
+          } else if (kb < kb8) {
             // scale factors of this k-block: shared memory -> 4 + 4 tensor-memory columns (tcgen05.cp and tcgen05.mma execute in
             // issue order, so the copies are complete before the MMAs below read them; two buffers alternate anyway)
             const uint32_t sfa_t = tmem_base + kSfCol0 + sfbuf * 8, sfb_t = sfa_t + 4;
@@ -209,18 +214,21 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t db = B_MN ? desc8_mn(sb, k) : desc8_k(sb, k);
               umma_mx_ss(d_tmem, da, db, make_idesc_mx(BM, BN, B_MN ? 1 : 0, k, k), sfa_t | (k << 30), sfb_t | (k << 30), (kb | (int)k) != 0);
             }
-            sfbuf ^= 1;
+            umma_commit(&empty_bar[stage]);
           } else {
 #pragma unroll
             for (int k = 0; k < KB16 / 16; ++k) umma_f16_ss(d_tmem, desc16_k(sa, k), desc16_k(sb, k), idesc16, 1u);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          if (kb < kb8) sfbuf ^= 1;
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
