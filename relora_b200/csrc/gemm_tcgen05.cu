@@ -648,346 +648,6 @@ struct LoraDxArgs {
   uint32_t keys[3];
 };
 
-template <int G>
-__global__ void __launch_bounds__(kNumThreads, 1)
-lora_dx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_a,
-               const __grid_constant__ CUtensorMap map_out, const LoraDxArgs p) {
-  constexpr int BLOCK_N = 128;
-  using L = SmemLayout<BLOCK_N>;
-  constexpr int kStages = L::kStages;
-  constexpr int kBaseStages = (G <= 2) ? 2 : 1;  // TMEM budget: (kBaseStages + kLoraStages·G) · 128 <= 512 columns
-  constexpr int kLoraStages = (G == 1) ? 2 : 1;
-  constexpr uint32_t kTmemCols = 512;
-  static_assert((kBaseStages + kLoraStages * G) * BLOCK_N <= 512, "tensor memory budget");
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* lora_full = empty_bar + kStages;
-  uint64_t* lora_empty = lora_full + 2;
-  uint64_t* base_full = lora_empty + 2;
-  uint64_t* base_empty = base_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(base_empty + 2);
-
-  const uint32_t warp = warp_id();
-  const uint32_t lane = lane_id();
-  if (threadIdx.x == 0) pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_dy);
-    tma_prefetch_desc(&map_w);
-    tma_prefetch_desc(&map_du);
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_out);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&lora_full[a], 1);
-      mbar_init(&lora_empty[a], 128);
-      mbar_init(&base_full[a], 1);
-      mbar_init(&base_empty[a], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_base_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-  pdl_wait();
-
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kb_lora = p.r / BLOCK_K;                     // r is a multiple of 64
-  const int kb_base = (p.Kb + BLOCK_K - 1) / BLOCK_K;
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < G * kb_lora; ++kb) {  // du [M, G·r] K-major ; A [G·r, N] MN-major
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_du, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_a, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
-          advance();
-        }
-        for (int kb = 0; kb < kb_base; ++kb) {      // dy [M, Kb] K-major ; W [Kb, N] MN-major
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          load_operand<BLOCK_M, false>(&map_dy, smem_u32(&full_bar[stage]), sa, m0, kb * BLOCK_K, kEvictNormal);
-          load_operand<BLOCK_N, true>(&map_w, smem_u32(&full_bar[stage]), sa + L::kABytes, n0, kb * BLOCK_K, kEvictLast);
-          advance();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      int ls = 0, bs = 0;
-      uint32_t ls_phase = 0, bs_phase = 0;
-      auto mma_block = [&](uint32_t d_tmem, bool first) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t sb = sa + L::kABytes;
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_f16_ss(d_tmem, operand_desc<false>(sa, k), operand_desc<true>(sb, k), idesc, !(first && k == 0));
-        umma_commit(&empty_bar[stage]);
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&lora_empty[ls], ls_phase ^ 1);
-        tc_fence_after();
-        for (int g = 0; g < G; ++g) {
-          const uint32_t d_tmem = tmem_base + (kBaseStages + ls * G + g) * BLOCK_N;
-          for (int kb = 0; kb < kb_lora; ++kb) mma_block(d_tmem, kb == 0);
-        }
-        umma_commit(&lora_full[ls]);
-        if (kb_base > 0) {
-          mbar_wait(&base_empty[bs], bs_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + bs * BLOCK_N;
-          for (int kb = 0; kb < kb_base; ++kb) mma_block(d_tmem, kb == 0);
-          umma_commit(&base_full[bs]);
-        }
-        if (++ls == kLoraStages) {
-          ls = 0;
-          ls_phase ^= 1;
-        }
-        if (++bs == kBaseStages) {
-          bs = 0;
-          bs_phase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= kEpilogueWarp0) {
-    // ===================================================================== epilogue
-    const uint32_t quad = warp & 3;
-    const uint32_t et = threadIdx.x - kEpilogueWarp0 * 32;
-    const bool issuer = (et == 0);
-    uint8_t* stage_base = smem + L::kTileBytes + L::kBarrierBytes;
-    const uint32_t seed0 = p.seed_ptr ? *p.seed_ptr : 0u;
-    uint32_t seeds[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) seeds[g] = mix_seed(seed0, p.keys[g]);
-    int ls = 0, bs = 0;
-    uint32_t ls_phase = 0, bs_phase = 0;
-    int slab_counter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      const uint32_t row = m0 + quad * 32 + lane;
-      const uint32_t rowmix = row * 0x9E3779B1u;
-      // two-kernel form: this thread's row of the supplied frozen-path product (2 x 128 bytes) is requested *now*, so the
-      // ~1 us global-memory latency is covered by the LoRA MMAs and the mask hashing below instead of stalling every slab
-      uint4 bpre[2][8];
-      if (kb_base == 0) {
-        const bool row_in = (int)row < p.M;
-        const bf16* bp = p.base + (long long)row * p.ld_base + n0;
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            bpre[sl][q] = (row_in && n0 + sl * 64 + q * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(bp + sl * 64 + q * 8)
-                                                                         : make_uint4(0, 0, 0, 0);
-      }
-      if (kb_base == 0) {
-        // ---- two-kernel form, single phase: per 16 columns, all G accumulators are fetched with one TMEM round trip, masked,
-        // added to the prefetched frozen-path product and written straight into the output slab
-        mbar_wait(&lora_full[ls], ls_phase);
-        tc_fence_after();
-        const uint32_t rloc = quad * 32 + lane;
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          uint8_t* slab = stage_base + (slab_counter % L::kSlabs) * L::kSlabBytes;
-          uint8_t* rowp = slab + rloc * 128;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int ch = sl * 4 + c4;
-            uint32_t rr[G][16];
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-              tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + ch * 16), rr[g]);
-            tmem_ld_wait();
-            if (sl == 1 && c4 == 3) {  // last read of the accumulators: hand them back to the MMA warp
-              tc_fence_before();
-              mbar_arrive(&lora_empty[ls]);
-            }
-            float cf[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cf[i] = 0.f;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const uint32_t sg = rowmix ^ seeds[g];
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                const uint32_t cp = (uint32_t)(n0 + ch * 16 + i) >> 1;
-                const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
-                if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[g][i]);
-                if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[g][i + 1]);
-              }
-            }
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              float f[8];
-              unpack8(bpre[sl][c4 * 2 + h2], f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaf(cf[h2 * 8 + i], p.inv_keep, f[i]);
-              const int q = c4 * 2 + h2;
-              *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = pack8(f);
-            }
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (issuer) {
-            tma_store_2d(&map_out, slab, n0 + sl * 64, m0);
-            tma_store_commit();
-            tma_store_wait_read<L::kSlabs - 2>();
-          }
-          ++slab_counter;
-        }
-        if (++ls == kLoraStages) {
-          ls = 0;
-          ls_phase ^= 1;
-        }
-        continue;
-      }
-      // ---- phase 1: masked sum of the LoRA accumulators, packed to bf16x2 (overlaps the frozen-path MMAs)
-      uint32_t cpk[BLOCK_N / 2];
-      mbar_wait(&lora_full[ls], ls_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < BLOCK_N / 16; ++ch) {
-        float cf[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cf[i] = 0.f;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          uint32_t rr[16];
-          tmem_ld_32x32b_x16(tmem_addr(tmem_base, quad * 32, (kBaseStages + ls * G + g) * BLOCK_N + ch * 16), rr);
-          tmem_ld_wait();
-          const uint32_t sg = rowmix ^ seeds[g];
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {  // one hash per column pair (common.cuh:keep_drop)
-            const uint32_t cp = (uint32_t)(n0 + ch * 16 + i) >> 1;
-            const uint32_t hsh = lowbias32(sg ^ (cp * 0x85EBCA77u));
-            if ((hsh & 0xFFFFu) >= p.thr16) cf[i] += __uint_as_float(rr[i]);
-            if ((hsh >> 16) >= p.thr16) cf[i + 1] += __uint_as_float(rr[i + 1]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cpk[ch * 8 + i] = pack_bf16x2(cf[2 * i] * p.inv_keep, cf[2 * i + 1] * p.inv_keep);
-      }
-      tc_fence_before();
-      mbar_arrive(&lora_empty[ls]);
-      // ---- phase 2: frozen-path accumulator + combined LoRA term -> bf16 slab -> TMA store
-      if (kb_base > 0) {
-        mbar_wait(&base_full[bs], bs_phase);
-        tc_fence_after();
-      }
-#pragma unroll
-      for (int sl = 0; sl < BLOCK_N / 64; ++sl) {
-        uint8_t* slab = stage_base + (slab_counter % L::kSlabs) * L::kSlabBytes;  // freed by wait_read two iterations ago
-        uint4 packed[8];
-        if (kb_base > 0) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64), r0);
-          tmem_ld_32x32b_x32(tmem_addr(tmem_base, quad * 32, bs * BLOCK_N + sl * 64 + 32), r1);
-          tmem_ld_wait();
-          if (sl == BLOCK_N / 64 - 1) {
-            tc_fence_before();
-            mbar_arrive(&base_empty[bs]);
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
-              const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-              const uint32_t raw0 = (q < 4) ? r0[q * 8 + i] : r1[(q - 4) * 8 + i];
-              const uint32_t raw1 = (q < 4) ? r0[q * 8 + i + 1] : r1[(q - 4) * 8 + i + 1];
-              f[i] = __uint_as_float(raw0) + c2.x;
-              f[i + 1] = __uint_as_float(raw1) + c2.y;
-            }
-            packed[q] = pack8(f);
-          }
-        } else {
-          // frozen-path product (prefetched at the top of the tile)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float f[8];
-            unpack8(bpre[sl][q], f);
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const uint32_t pk = cpk[sl * 32 + q * 4 + i / 2];
-              const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-              f[i] += c2.x;
-              f[i + 1] += c2.y;
-            }
-            packed[q] = pack8(f);
-          }
-        }
-        const uint32_t rloc = quad * 32 + lane;
-        uint8_t* rowp = slab + rloc * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(rowp + ((q ^ (rloc & 7)) << 4)) = packed[q];
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (issuer) {
-          tma_store_2d(&map_out, slab, n0 + sl * 64, m0);
-          tma_store_commit();
-          tma_store_wait_read<L::kSlabs - 2>();
-        }
-        ++slab_counter;
-      }
-      if (++ls == kLoraStages) {
-        ls = 0;
-        ls_phase ^= 1;
-      }
-      if (++bs == kBaseStages) {
-        bs = 0;
-        bs_phase ^= 1;
-      }
-    }
-    if (issuer) tma_store_wait<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 // One-kernel form (frozen-path product in the same kernel, Kb > 0) with TWO epilogue warpgroups, one per 64-column half of the tile.
 template <int G>
 __global__ void __launch_bounds__(384, 1)
@@ -1529,7 +1189,7 @@ lora_dx_pair_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
 //   dx[M,N] = base[M,N] + inv_keep · Σ_g keep_g(row, col) ⊙ ( du_g[M,r] · A_g[r,N] )
 //
 // The products are tiny (K = r per group); the work is the epilogue (G TMEM reads + one mask hash per column pair and
-// group).  ncu on the single-epilogue-warpgroup version (lora_dx_kernel, Kb == 0): ~3950 instructions per thread and tile,
+// group).  ncu on the round-1 single-epilogue-warpgroup version: ~3950 instructions per thread and tile,
 // one warp per scheduler, 7.3 stall cycles per issue (barrier 2.1, long scoreboard 1.4, instruction fetch 1.3) -> 41.7 us for
 // M 12288 x N 768, G = 3 (0.17 of the HBM roofline).  Here TWO epilogue warpgroups split every 128-column tile into its two
 // 64-column slabs (two warps per scheduler, half the instructions each, independent slabs / named barriers / TMA stores).
@@ -2023,17 +1683,13 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return;
-  static const bool split = [] {
-    const char* e = getenv("RB_LORA_DX_SPLIT");  // 0: single epilogue warpgroup (the round-1 kernel; A/B timing)
-    return e == nullptr || atoi(e) != 0;
-  }();
   static const bool pair_ok = [] {
     const char* e = getenv("RB_LORA_DX_PAIR");  // 0: single-CTA 128 x 128 tiles, 5 stages (lora_dx_fused2_kernel; A/B timing)
     return e == nullptr || atoi(e) != 0;
   }();
   // measured with the converged issue loops (bench/lora_dx_bench.py): pairs win from a reduction of ~2 K up (1b down dx 145 vs 156 us,
   // 250m qkv dx 45.5 vs 48.7), single CTAs below (250m down dx, Kb = 768: 55.8 vs 66.2 us)
-  if (d.Kb >= 1536 && split && pair_ok && d.M > BLOCK_M) {
+  if (d.Kb >= 1536 && pair_ok && d.M > BLOCK_M) {
     using LP = LoraPairSmem;
     auto kernp = lora_dx_pair_kernel<G>;
     static int max_clusters = 0;
@@ -2067,7 +1723,7 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
     RB_CHECK_LAUNCH("lora_dx_pair_kernel");
     return;
   }
-  if (d.Kb > 0 && split) {
+  {
     auto kern2 = lora_dx_fused2_kernel<G>;
     static bool configured2 = false;
     if (!configured2) {
@@ -2076,16 +1732,7 @@ static void launch_lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
     }
     launch_k(kern2, grid, 384, L::kTotal, stream, m_dy, m_w, m_du, m_a, m_out, p);
     RB_CHECK_LAUNCH("lora_dx_fused2_kernel");
-    return;
   }
-  auto kern = lora_dx_kernel<G>;
-  static bool configured = false;
-  if (!configured) {
-    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "cudaFuncSetAttribute(lora_dx)");
-    configured = true;
-  }
-  launch_k(kern, grid, kNumThreads, L::kTotal, stream, m_dy, m_w, m_du, m_a, m_out, p);
-  RB_CHECK_LAUNCH("lora_dx_kernel");
 }
 
 template <int G>
@@ -2121,11 +1768,7 @@ void lora_dx(const LoraDxDesc& d, cudaStream_t stream) {
   if (d.Kb == 0 && (d.base == nullptr || d.ld_base % 8 != 0 || (reinterpret_cast<uintptr_t>(d.base) & 15) != 0))
     throw std::runtime_error("lora_dx: Kb == 0 needs a 16-byte aligned base product");
   if (d.ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) throw std::runtime_error("lora_dx: output must be 16-byte aligned");
-  static const bool split_epilogue = [] {
-    const char* e = getenv("RB_LORA_DX_BASE_SPLIT");  // 0: the single-warpgroup epilogue of lora_dx_kernel (diagnostics / A-B timing)
-    return e == nullptr || atoi(e) != 0;
-  }();
-  if (d.Kb == 0 && split_epilogue) {  // frozen-path product supplied: the two-warpgroup epilogue kernel
+  if (d.Kb == 0) {  // frozen-path product supplied: mask-and-add kernel
     if (d.groups == 1) launch_lora_dx_base<1>(d, stream);
     else if (d.groups == 2) launch_lora_dx_base<2>(d, stream);
     else launch_lora_dx_base<3>(d, stream);
