@@ -1,5 +1,5 @@
 """Run the two-kernel form of the LoRA input gradient (frozen-path product supplied, `lora_dx ... Kb0 (+base)`) a few times
-(target for `ncu -k regex:lora_dx_kernel`).  Default shape: llama_250m qkv group (G = 3, N = 768)."""
+(target for `ncu -k regex:lora_dx_base`).  Default shape: llama_250m qkv group (G = 3, N = 768)."""
 import argparse, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from relora_b200.ops import fused as F

@@ -1,4 +1,4 @@
-"""Run the fused LoRA input-gradient kernel a few times (target for `ncu -k regex:lora_dx_kernel`)."""
+"""Run the fused LoRA input-gradient kernel a few times (target for `ncu -k regex:lora_dx_fused2` or `regex:lora_dx_pair`)."""
 import argparse, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from relora_b200.ops import fused as F
